@@ -1,0 +1,232 @@
+"""ctypes binding of the CPU ORACLE (oracle/rolo_oracle.h). Test infrastructure only.
+
+Importers allowed: tests/, __graft_entry__.smoke(), bench.py (cpu_baseline / --impl reference).
+The product package rolo_b200/ must never import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "librolo_oracle.so")
+
+REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS, REG_PLANE_S = range(6)
+DIRECT27, DIRECT7, DIRECT1, DIRECT_RADIUS = range(4)
+VOXEL_POLAR, VOXEL_UNIFORM = range(2)
+OPT_GAUSS_NEWTON, OPT_LM, OPT_SO3_LM = range(3)
+
+_dp = C.POINTER(C.c_double)
+_fp = C.POINTER(C.c_float)
+_ip = C.POINTER(C.c_int)
+
+
+def build(force: bool = False) -> str:
+    src = [os.path.join(_HERE, f) for f in ("rolo_oracle.cpp", "rolo_oracle.h", "frontend_oracle.cpp", "Makefile")]
+    stale = force or not os.path.exists(_LIB_PATH) or any(
+        os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
+    if stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        L.ro_create.restype = C.c_void_p
+        for name in ("ro_linearize", "ro_so3_linearize", "ro_compute_error", "ro_t3_linearize", "ro_compute_t_error"):
+            getattr(L, name).restype = C.c_double
+        for name in ("ro_get_covariances", "ro_voxel_count", "ro_num_correspondences", "ro_trace_size"):
+            getattr(L, name).restype = C.c_size_t
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_dp)
+
+
+class Oracle:
+    """Thin object wrapper; method names follow the reference class (rot_vgicp.hpp:72-104)."""
+
+    def __init__(self):
+        self.L = lib()
+        self.h = C.c_void_p(self.L.ro_create())
+        self._keep = []
+
+    def __del__(self):
+        try:
+            self.L.ro_destroy(self.h)
+        except Exception:
+            pass
+
+    # --- configuration -------------------------------------------------------------
+    def setNumThreads(self, n): self.L.ro_set_num_threads(self.h, C.c_int(n))
+    def getNumThreads(self): return self.L.ro_get_num_threads(self.h)
+    def setResolution(self, r): self.L.ro_set_resolution(self.h, C.c_double(r))
+    def setPolarResolution(self, th, ph, r): self.L.ro_set_polar_resolution(self.h, C.c_double(th), C.c_double(ph), C.c_double(r))
+    def setNeighborSearchMethod(self, m): self.L.ro_set_neighbor_search_method(self.h, C.c_int(m))
+    def setRegularizationMethod(self, m): self.L.ro_set_regularization_method(self.h, C.c_int(m))
+    def setCorrespondenceRandomness(self, k): self.L.ro_set_correspondence_randomness(self.h, C.c_int(k))
+    def setOptimizerType(self, t): self.L.ro_set_optimizer_type(self.h, C.c_int(t))
+    def setMaximumIterations(self, n): self.L.ro_set_max_iterations(self.h, C.c_int(n))
+    def setRotationEpsilon(self, e): self.L.ro_set_rotation_epsilon(self.h, C.c_double(e))
+    def setTransformationEpsilon(self, e): self.L.ro_set_transformation_epsilon(self.h, C.c_double(e))
+    def setInitialLambdaFactor(self, f): self.L.ro_set_initial_lambda_factor(self.h, C.c_double(f))
+
+    # --- clouds ----------------------------------------------------------------------
+    def _cloud(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        assert pts.ndim == 2 and pts.shape[1] >= 3
+        return pts
+
+    def setInputSource(self, pts):
+        pts = self._cloud(pts)
+        self.L.ro_set_input_source(self.h, pts.ctypes.data_as(_fp), C.c_size_t(pts.shape[0]), C.c_size_t(pts.shape[1]))
+        self.n_src = pts.shape[0]
+
+    def setInputTarget(self, pts):
+        pts = self._cloud(pts)
+        self.L.ro_set_input_target(self.h, pts.ctypes.data_as(_fp), C.c_size_t(pts.shape[0]), C.c_size_t(pts.shape[1]))
+        self.n_tgt = pts.shape[0]
+
+    def setSourceCovariances(self, covs): self._set_covs(0, covs)
+    def setTargetCovariances(self, covs): self._set_covs(1, covs)
+
+    def _set_covs(self, which, covs):
+        covs = np.ascontiguousarray(covs, dtype=np.float64).reshape(-1, 16)
+        self.L.ro_set_covariances(self.h, C.c_int(which), _d(covs), C.c_size_t(covs.shape[0]))
+
+    def calculateCovariances(self, which):
+        return self.L.ro_calculate_covariances(self.h, C.c_int(which))
+
+    def getCovariances(self, which):
+        n = self.L.ro_get_covariances(self.h, C.c_int(which), None)
+        out = np.empty((n, 4, 4), dtype=np.float64)
+        self.L.ro_get_covariances(self.h, C.c_int(which), _d(out))
+        return out
+
+    def getSourceCovariances(self): return self.getCovariances(0)
+    def getTargetCovariances(self): return self.getCovariances(1)
+
+    def knn(self, which, k):
+        n = self.n_src if which == 0 else self.n_tgt
+        out = np.empty((n, k), dtype=np.int32)
+        self.L.ro_knn(self.h, C.c_int(which), C.c_int(k), out.ctypes.data_as(_ip))
+        return out
+
+    # --- voxel map ---------------------------------------------------------------------
+    def createVoxelmap(self): self.L.ro_create_voxelmap(self.h)
+    def resetVoxelmap(self): self.L.ro_reset_voxelmap(self.h)
+
+    def getVoxels(self):
+        v = self.L.ro_voxel_count(self.h)
+        keys = np.empty((v, 3), dtype=np.int32)
+        mean = np.empty((v, 4), dtype=np.float64)
+        cov = np.empty((v, 4, 4), dtype=np.float64)
+        npts = np.empty((v,), dtype=np.int32)
+        self.L.ro_get_voxels(self.h, keys.ctypes.data_as(_ip), _d(mean), _d(cov), npts.ctypes.data_as(_ip))
+        return keys, mean, cov, npts
+
+    # --- hot-path evaluations ------------------------------------------------------------
+    @staticmethod
+    def _T(T):
+        return np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+
+    def linearize(self, T, want_H=True):
+        T = self._T(T)
+        if not want_H:
+            return self.L.ro_linearize(self.h, _d(T), None, None), None, None
+        H = np.empty((6, 6)); b = np.empty(6)
+        c = self.L.ro_linearize(self.h, _d(T), _d(H), _d(b))
+        return c, H, b
+
+    def so3_linearize(self, T):
+        T = self._T(T)
+        H = np.empty((3, 3)); b = np.empty(3)
+        c = self.L.ro_so3_linearize(self.h, _d(T), _d(H), _d(b))
+        return c, H, b
+
+    def compute_error(self, T):
+        T = self._T(T)
+        return self.L.ro_compute_error(self.h, _d(T))
+
+    def t3_linearize(self, t, guess, last_t0, dtn, dtn1):
+        t, g, l = (np.ascontiguousarray(x, dtype=np.float64) for x in (t, guess, last_t0))
+        H = np.empty((6, 6)); b = np.empty(6)
+        c = self.L.ro_t3_linearize(self.h, _d(t), _d(g), _d(l), C.c_double(dtn), C.c_double(dtn1), _d(H), _d(b))
+        return c, H, b
+
+    def compute_t_error(self, t, guess, last_t0, dtn, dtn1):
+        t, g, l = (np.ascontiguousarray(x, dtype=np.float64) for x in (t, guess, last_t0))
+        return self.L.ro_compute_t_error(self.h, _d(t), _d(g), _d(l), C.c_double(dtn), C.c_double(dtn1))
+
+    def setCtLambda(self, lam): self.L.ro_set_ct_lambda(self.h, C.c_float(lam))
+
+    def getCorrespondences(self):
+        m = self.L.ro_num_correspondences(self.h)
+        idx = np.empty((m,), dtype=np.int32); key = np.empty((m, 3), dtype=np.int32)
+        self.L.ro_get_correspondences(self.h, idx.ctypes.data_as(_ip), key.ctypes.data_as(_ip))
+        return idx, key
+
+    # --- drivers ---------------------------------------------------------------------------
+    def align(self, guess=None):
+        g = np.eye(4, dtype=np.float32) if guess is None else np.ascontiguousarray(guess, dtype=np.float32)
+        out = np.empty((4, 4), dtype=np.float32)
+        self.rc = self.L.ro_align(self.h, g.ctypes.data_as(_fp), out.ctypes.data_as(_fp))
+        self.final_transformation = out
+        return out
+
+    def getFinalTransformation(self): return self.final_transformation
+
+    def getFinalPoseDouble(self):
+        T = np.empty((4, 4)); self.L.ro_get_final_pose_d(self.h, _d(T)); return T
+
+    def hasConverged(self): return bool(self.L.ro_has_converged(self.h))
+    def nrIterations(self): return self.L.ro_nr_iterations(self.h)
+
+    def getFinalHessian(self):
+        H = np.empty((6, 6)); self.L.ro_get_final_hessian(self.h, _d(H)); return H
+
+    def computeTranslation(self, trans, init_guess, last_t0, dtn, dtn1, ct_lambda):
+        t = np.array(trans, dtype=np.float64)
+        g, l = (np.ascontiguousarray(x, dtype=np.float64) for x in (init_guess, last_t0))
+        self.rc = self.L.ro_compute_translation(self.h, _d(t), _d(g), _d(l), C.c_double(dtn), C.c_double(dtn1), C.c_float(ct_lambda))
+        return t
+
+    def getTrace(self):
+        n = self.L.ro_trace_size(self.h)
+        out = np.empty((n, 64), dtype=np.float64)
+        if n:
+            self.L.ro_get_trace(self.h, _d(out))
+        return out
+
+
+def so3_exp(w):
+    w = np.ascontiguousarray(w, dtype=np.float64); q = np.empty(4)
+    lib().ro_so3_exp(_d(w), _d(q)); return q
+
+
+def se3_exp(a):
+    a = np.ascontiguousarray(a, dtype=np.float64); T = np.empty((4, 4))
+    lib().ro_se3_exp(_d(a), _d(T)); return T
+
+
+def svd3(A):
+    A = np.ascontiguousarray(A, dtype=np.float64); U = np.empty((3, 3)); S = np.empty(3); V = np.empty((3, 3))
+    lib().ro_svd3(_d(A), _d(U), _d(S), _d(V)); return U, S, V
+
+
+def ldlt_solve(A, b):
+    A = np.ascontiguousarray(A, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.empty_like(b)
+    lib().ro_ldlt_solve(_d(A), _d(b), C.c_int(b.shape[0]), _d(x)); return x
