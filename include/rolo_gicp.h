@@ -1,0 +1,199 @@
+/*
+ * rolo_gicp.h — C-ABI of the B200-native voxelized-GICP core (librolo_gicp_b200.so).
+ *
+ * This is the drop-in boundary for the one data-parallel hot path of sdwyc/ROLO: the
+ * fast_gicp::RotVGICP scan matcher ("rot_gicp") plus the two upstream range-image passes.
+ * Every entry point replaces one reference interface (cited file:line, paths relative to the
+ * reference checkout). The C++ class template in include/rot_gicp/gicp/rot_vgicp.hpp forwards to
+ * these; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types; all functions return 0 on success and a
+ *    negative rg_status on failure (no exception crosses the ABI); rg_last_error() gives text.
+ *  - matrices are ROW-MAJOR. Poses are 4x4 (16 values); H6 = 6x6 (36), b6 = 6; H3 = 3x3 (9), b3 = 3.
+ *    (Eigen is column-major: the C++ wrapper transposes; H is symmetric.)
+ *  - "host" pointers are ordinary host memory; "_device" variants take device pointers of the
+ *    context's GPU and a cudaStream_t passed as void* (0 = the context's own stream).
+ *  - enum values equal the reference's enum class order (gicp_settings.hpp:6-12,
+ *    lsq_registration.hpp:13) so the C++ wrapper can static_cast.
+ *  - the CUDA device is mandatory: there is NO CPU fallback; rg_create fails without a GPU.
+ */
+#ifndef ROLO_GICP_H
+#define ROLO_GICP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ROLO_GICP_ABI_VERSION 1
+
+typedef struct rg_ctx rg_ctx;      /* one registration object == one fast_gicp::RotVGICP instance   */
+typedef struct rg_batch rg_batch;  /* a lock-step batch of independent scan pairs on one GPU         */
+
+typedef enum rg_status {
+  RG_OK = 0,
+  RG_ERR_INVALID = -1,      /* bad argument / call order (maps to std::invalid_argument)            */
+  RG_ERR_CUDA = -2,         /* CUDA runtime error (maps to std::runtime_error)                      */
+  RG_ERR_NO_DEVICE = -3,    /* no usable GPU: the product path refuses to run                       */
+  RG_ERR_UNSUPPORTED = -4,  /* enum value the reference abort()s on (voxel.hpp:16-18, impl.hpp:472) */
+  RG_ERR_NOT_CONVERGED = -5 /* "lm not converged!!" break (lsq.hpp:66-69,168-171); pose still valid */
+} rg_status;
+
+/* gicp_settings.hpp:6 */
+enum { RG_REG_NONE = 0, RG_REG_MIN_EIG, RG_REG_NORMALIZED_MIN_EIG, RG_REG_PLANE, RG_REG_FROBENIUS, RG_REG_PLANE_S };
+/* gicp_settings.hpp:8 */
+enum { RG_DIRECT27 = 0, RG_DIRECT7, RG_DIRECT1, RG_DIRECT_RADIUS };
+/* gicp_settings.hpp:10 */
+enum { RG_ACC_ADDITIVE = 0, RG_ACC_ADDITIVE_WEIGHTED, RG_ACC_MULTIPLICATIVE };
+/* gicp_settings.hpp:12 */
+enum { RG_VOXEL_POLAR = 0, RG_VOXEL_UNIFORM };
+/* lsq_registration.hpp:13 */
+enum { RG_OPT_GAUSS_NEWTON = 0, RG_OPT_LM, RG_OPT_SO3_LM };
+enum { RG_SOURCE = 0, RG_TARGET = 1 };
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+int  rg_abi_version(void);
+/* RotVGICP::RotVGICP() (rot_vgicp_impl.hpp:20-39) + LsqRegistration() (lsq_registration_impl.hpp:9-24):
+ * same defaults. device < 0 => current CUDA device. Device buffers come from a process-global pool
+ * because the caller constructs a fresh object every frame (lidarOdometry.cpp:460). */
+int  rg_create(int device, rg_ctx** out);
+void rg_destroy(rg_ctx* ctx);                               /* ~RotVGICP (rot_vgicp_impl.hpp:42)     */
+const char* rg_last_error(const rg_ctx* ctx);               /* ctx may be NULL: last global error    */
+int  rg_device_count(void);
+
+/* ---- setters (rot_vgicp.hpp:72-93, lsq_registration.hpp:51-62, pcl::Registration) -------------- */
+int rg_set_resolution(rg_ctx*, double resolution);                         /* rot_vgicp_impl.hpp:45-49  */
+int rg_set_polar_resolution(rg_ctx*, double theta, double phi, double r);  /* rot_vgicp_impl.hpp:52-56  */
+int rg_set_voxel_accumulation_mode(rg_ctx*, int mode);                     /* rot_vgicp_impl.hpp:64-66  */
+int rg_set_neighbor_search_method(rg_ctx*, int method);                    /* rot_vgicp_impl.hpp:59-61  */
+int rg_set_num_threads(rg_ctx*, int n);                                    /* rot_vgicp_impl.hpp:79-87 (kept for API parity; ignored) */
+int rg_set_correspondence_randomness(rg_ctx*, int k);                      /* rot_vgicp_impl.hpp:90-92  */
+int rg_set_regularization_method(rg_ctx*, int method);                     /* rot_vgicp_impl.hpp:95-97  */
+int rg_set_optimizer_type(rg_ctx*, int type);                              /* lsq_registration_impl.hpp:338-340 */
+int rg_set_rotation_epsilon(rg_ctx*, double eps);                          /* lsq_registration_impl.hpp:30-32   */
+int rg_set_transformation_epsilon(rg_ctx*, double eps);                    /* pcl::Registration::setTransformationEpsilon */
+int rg_set_maximum_iterations(rg_ctx*, int n);                             /* pcl::Registration::setMaximumIterations     */
+int rg_set_initial_lambda_factor(rg_ctx*, double f);                       /* lsq_registration_impl.hpp:35-37   */
+int rg_set_debug_print(rg_ctx*, int on);                                   /* lsq_registration_impl.hpp:40-42   */
+
+/* ---- clouds ------------------------------------------------------------------------------------ */
+/* setInputSource / setInputTarget (rot_vgicp_impl.hpp:111-120, 132-143). xyz are the first three
+ * floats of each point; stride_bytes = sizeof(PointT) (32 for pcl::PointXYZI, 16 for PointXYZ).
+ * The data is copied to the device (H2D on the context's stream) before the call returns.      */
+int rg_set_input_source(rg_ctx*, const float* host_points, size_t n, size_t stride_bytes);
+int rg_set_input_target(rg_ctx*, const float* host_points, size_t n, size_t stride_bytes);
+/* same, from device-resident float4 (x,y,z,*) arrays: no host traffic */
+int rg_set_input_source_device(rg_ctx*, const float* dev_xyzw, size_t n, void* stream);
+int rg_set_input_target_device(rg_ctx*, const float* dev_xyzw, size_t n, void* stream);
+int rg_clear_source(rg_ctx*);                                              /* rot_vgicp_impl.hpp:99-103  */
+int rg_clear_target(rg_ctx*);                                              /* rot_vgicp_impl.hpp:105-109 */
+int rg_swap_source_and_target(rg_ctx*);                                    /* rot_vgicp_impl.hpp:68-76   */
+size_t rg_source_size(const rg_ctx*);
+size_t rg_target_size(const rg_ctx*);
+
+/* setSourceCovariances / setTargetCovariances (rot_vgicp_impl.hpp:122-130): n 4x4 double matrices */
+int rg_set_covariances(rg_ctx*, int which, const double* cov4x4, size_t n);
+/* getSourceCovariances / getTargetCovariances (rot_vgicp.hpp:94-100): returns count; writes n*16
+ * doubles when out != NULL. Device storage is 6 x fp32 per point.               */
+size_t rg_get_covariances(rg_ctx*, int which, double* out_cov4x4);
+
+/* ---- stages of computeTransformation ------------------------------------------------------------ */
+/* RotVGICP::calculate_covariances (rot_vgicp_impl.hpp:421-496): exact kNN(k) + regularised covariance */
+int rg_calculate_covariances(rg_ctx*, int which);
+/* VmfVoxelMap::create_voxelmap (vmp_voxel.hpp:167-197) over the target cloud + covariances        */
+int rg_create_voxelmap(rg_ctx*);
+/* RotVGICP::linearize (rot_vgicp_impl.hpp:224-290) = update_correspondences (172-222) + 6-DoF normal
+ * equations, one fused kernel. H36/b6 may be NULL (cost only, as evaluateCost allows).          */
+int rg_linearize(rg_ctx*, const double T[16], double* H36, double* b6, double* cost);
+/* RotVGICP::so3_linearize (rot_vgicp_impl.hpp:292-388)                                             */
+int rg_so3_linearize(rg_ctx*, const double T[16], double* H9, double* b3, double* cost);
+/* RotVGICP::compute_error (rot_vgicp_impl.hpp:390-417): cached correspondences + Mahalanobis      */
+int rg_compute_error(rg_ctx*, const double T[16], double* cost);
+/* RotVGICP::t3_linearize (rot_vgicp_impl.hpp:498-607) / compute_t_error (609-658)                  */
+int rg_t3_linearize(rg_ctx*, const double t[3], const double init_guess[3], const double last_t0[3],
+                    double interval_tn, double interval_tn_1, double* H36, double* b6, double* cost);
+int rg_compute_t_error(rg_ctx*, const double t[3], const double init_guess[3], const double last_t0[3],
+                       double interval_tn, double interval_tn_1, double* cost);
+int rg_set_ct_lambda(rg_ctx*, float lambda);                 /* lambda_ member, rot_vgicp_impl.hpp:166 */
+size_t rg_num_correspondences(const rg_ctx*);                /* voxel_correspondences_.size()          */
+
+/* ---- drivers -------------------------------------------------------------------------------------- */
+/* pcl::Registration::align(output, guess) -> RotVGICP::computeTransformation (rot_vgicp_impl.hpp:146-160)
+ * -> LsqRegistration::computeTransformation (lsq_registration_impl.hpp:152-179). The GN/LM step logic
+ * (6x6 / 3x3 LDLT, damping, convergence) runs on the host, one fused kernel per evaluation.
+ * Returns RG_OK or RG_ERR_NOT_CONVERGED (pose is written in both cases, as the reference does).  */
+int rg_align(rg_ctx*, const float guess[16], float final_transformation[16]);
+/* RotVGICP::computeTranslation (rot_vgicp_impl.hpp:162-169 -> lsq_registration_impl.hpp:55-80)     */
+int rg_compute_translation(rg_ctx*, double trans[3], const double init_guess[3], const double last_t0[3],
+                           double interval_tn, double interval_tn_1, float ct_lambda);
+/* pcl::transformPointCloud(*input_, output, T) (lsq_registration_impl.hpp:78,178): writes n points,
+ * xyz transformed, to host memory with the given stride (other bytes untouched).                  */
+int rg_transform_source(rg_ctx*, const float T[16], float* host_out, size_t stride_bytes);
+int rg_has_converged(const rg_ctx*);                          /* pcl::Registration::hasConverged       */
+int rg_nr_iterations(const rg_ctx*);
+int rg_get_final_hessian(const rg_ctx*, double H36[36]);      /* lsq_registration_impl.hpp:45-47       */
+int rg_get_final_pose(const rg_ctx*, double T[16]);           /* x0 in double, before the float cast   */
+
+/* ---- introspection used by the parity tests --------------------------------------------------------- */
+size_t rg_voxel_count(const rg_ctx*);
+/* voxels sorted by key: keys int32[V*3], mean double[V*3], cov6 double[V*6] (xx,xy,xz,yy,yz,zz), npts int32[V] */
+int rg_get_voxels(rg_ctx*, int32_t* keys, double* mean, double* cov6, int32_t* npts);
+/* cached correspondence voxel key per (source point, offset): int32[n*noff*3], INT32_MIN rows = none */
+int rg_get_correspondence_keys(rg_ctx*, int32_t* keys);
+/* exact kNN indices (k nearest incl. self, ascending (distance, index)): int32[n*k] */
+int rg_knn(rg_ctx*, int which, int k, int32_t* out_idx);
+/* kernel time of the last linearize/compute_error launch in microseconds (CUDA events), or <0 */
+double rg_last_kernel_us(const rg_ctx*);
+int rg_set_profile(rg_ctx*, int on);
+
+/* ---- batch of independent scan pairs (BASELINE config 3; one rg_batch per GPU, no collective) ------- */
+int  rg_batch_create(int device, int n_pairs, rg_batch** out);
+void rg_batch_destroy(rg_batch*);
+rg_ctx* rg_batch_ctx(rg_batch*, int pair);      /* per-pair context for setters / inputs / results  */
+/* align() of every pair in lock step: per stage ONE launch covers all pairs
+ * (covariances, voxel maps, then one fused linearize launch per GN/LM evaluation).              */
+int  rg_batch_align(rg_batch*, const float* guesses /* n_pairs*16 or NULL */, float* final_transformations /* n_pairs*16 */);
+double rg_batch_last_linearize_us(const rg_batch*);   /* mean device time of the fused launches (CUDA events) */
+int    rg_batch_last_linearize_launches(const rg_batch*);
+
+/* ---- sharded single registration (BASELINE config 4): reduction hook ----------------------------------
+ * When set, every linearize/compute_error result (32 doubles: 28 packed sums + count + pad) is passed
+ * through `fn` before the host step, so N ranks each holding a shard of the source cloud behave as one
+ * registration. on_device != 0: buf is a device pointer (NCCL path); else host pointer (gloo / tests).   */
+typedef int (*rg_reduce_fn)(void* user, double* buf, int count, int on_device, void* stream);
+int rg_set_reduce_hook(rg_ctx*, rg_reduce_fn fn, void* user, int on_device);
+
+/* ---- upstream range-image passes ------------------------------------------------------------------------ */
+/* ImageProjection::projectPointCloud + cloudExtraction (imageProjection.cpp:399-505), deskew disabled
+ * (config/params.yaml:25). Raw points: x,y,z float at byte offsets 0,4,8; ring uint16 at ring_offset.
+ * Outputs (host): range image float[n_scan*horizon] (FLT_MAX = empty), extracted cloud float4 xyz+intensity
+ * (intensity = ring*z, imageProjection.cpp:410), point_col_ind int32, point_range float, start/end ring index. */
+typedef struct rg_projection_params {
+  int n_scan, horizon_scan, downsample_rate;
+  float lidar_min_range, lidar_max_range;
+  int point_stride_bytes, ring_offset_bytes;
+} rg_projection_params;
+int rg_image_projection(rg_ctx*, const void* host_raw_points, size_t n_points, const rg_projection_params* p,
+                        float* range_image, float* extracted_xyzi, int32_t* point_col_ind, float* point_range,
+                        int32_t* start_ring_index, int32_t* end_ring_index, int32_t* n_extracted);
+
+/* FeatureExtraction::calculateSmoothness / markOccludedPoints / extractFeatures
+ * (featureExtraction.cpp:87-266). Inputs are rg_image_projection's outputs.
+ * Outputs: curvature float[n], neighbor_picked int32[n], label int32[n] after extraction,
+ * corner cloud float4[<=n] and (un-downsampled) surface candidate mask.                          */
+typedef struct rg_feature_params {
+  int n_scan, horizon_scan;
+  float edge_threshold, surf_threshold, surf_leaf_size;
+} rg_feature_params;
+int rg_feature_extraction(rg_ctx*, const float* extracted_xyzi, const int32_t* point_col_ind, const float* point_range,
+                          const int32_t* start_ring_index, const int32_t* end_ring_index, int32_t n_extracted,
+                          const rg_feature_params* p, float* curvature, int32_t* neighbor_picked, int32_t* label,
+                          float* corner_xyzi, int32_t* n_corner, float* surface_xyzi, int32_t* n_surface);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROLO_GICP_H */

@@ -1,0 +1,141 @@
+// common.cuh — shared device/host definitions of the B200 (sm_100a) voxelized-GICP core.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace rolo {
+
+// ---- data layout in HBM -------------------------------------------------------
+// points   : float4 xyzw[Npad]           (w = 1; Npad = N rounded up to TILE_PTS, pad = far sentinel)
+// cov6     : tile-planar float: tile b (TILE_PTS points) holds 6 planes [xx|xy|xz|yy|yz|zz] of
+//            TILE_PTS floats each, i.e. element (i, c) at  (i / TILE) * 6*TILE + c*TILE + i % TILE.
+//            One 1-D TMA bulk copy moves a whole tile (6 KB); shared-memory reads are conflict-free.
+// table    : open-addressing hash, VoxSlot[cap] (16 B), cap = pow2 >= 2 * Ntarget
+// payload  : VoxPayload[V] (80 B, fp64): mean, covariance (6 unique), w = sqrt(n)
+constexpr int TILE_PTS = 256;          // points per TMA tile == threads per CTA in the fused kernel
+constexpr int COV_PLANES = 6;
+constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr int KEY_BIAS = 1 << 20;      // 21 bits per axis
+
+struct __align__(16) VoxSlot {
+  unsigned long long key;   // packed biased (x,y,z), KEY_EMPTY = free
+  int id;                   // compact voxel index into the payload array, -1 until assigned
+  int pad;
+};
+
+struct __align__(16) VoxPayload {
+  double mean[3];
+  double cov[6];            // xx xy xz yy yz zz (mean of the member points' covariances, voxel.hpp:107)
+  double w;                 // sqrt(num_points) (impl.hpp:258)
+};
+
+struct VoxAccum {            // accumulation buffer (struct-of-arrays by field, fp64 atomics)
+  double* sum;               // [V_cap][10]: mean xyz (3), cov6 (6), count (1)
+};
+
+struct GridParams {
+  int voxel_type;            // RG_VOXEL_POLAR = 0 / RG_VOXEL_UNIFORM = 1
+  double res[3];             // polar (theta, phi, r) or uniform (res, res, res)
+  double inv_res[3];
+};
+
+// Result vector of one linearize / compute_error launch (per pair): 32 doubles.
+//  [0..5]   Mw   = sum w*s M            (xx xy xz yy yz zz)       -> H[3:6,3:6]
+//  [6..14]  G    = sum w*s M S          (row-major 3x3)           -> H[3:6,0:3] = -G, H[0:3,3:6] = -G^T
+//  [15..20] StG  = sum w*s S^T M S      (xx xy xz yy yz zz)       -> H[0:3,0:3]
+//  [21..23] q    = sum w M e_b                                     -> b[3:6] = -q
+//  [24..26] Stq  = sum w S^T M e_b                                 -> b[0:3]
+//  [27]     cost = sum w (e^T M e + lam_c ct^T M ct)
+//  [28]     number of correspondences
+//  [29..31] reserved
+constexpr int RES_N = 32;
+constexpr int RES_USED = 29;
+
+inline __host__ __device__ unsigned long long pack_key(int x, int y, int z) {
+  return ((unsigned long long)(unsigned)(x + KEY_BIAS) << 42) | ((unsigned long long)(unsigned)(y + KEY_BIAS) << 21) |
+         (unsigned long long)(unsigned)(z + KEY_BIAS);
+}
+inline __host__ __device__ bool key_in_range(int x, int y, int z) {
+  return (unsigned)(x + KEY_BIAS) < (2u << 20) && (unsigned)(y + KEY_BIAS) < (2u << 20) && (unsigned)(z + KEY_BIAS) < (2u << 20);
+}
+inline __host__ __device__ void unpack_key(unsigned long long k, int& x, int& y, int& z) {
+  x = (int)((k >> 42) & 0x1FFFFF) - KEY_BIAS;
+  y = (int)((k >> 21) & 0x1FFFFF) - KEY_BIAS;
+  z = (int)(k & 0x1FFFFF) - KEY_BIAS;
+}
+inline __host__ __device__ unsigned hash_key(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+  return (unsigned)k;
+}
+
+#ifdef __CUDACC__
+// Voxel coordinate of a point given in double, bit-compatible with the reference:
+//  UNIFORM: floor(x/res - 0.5) per axis                      (vmp_voxel.hpp:199-201)
+//  POLAR  : floor([atan2(y,x)+pi, acos(z/r), r] / res)       (vmp_voxel.hpp:208-211)
+// Exact fp64 path (always correct, slow on the transcendental units).
+__device__ __forceinline__ void voxel_coord_exact(const GridParams& g, double x, double y, double z, int& cx, int& cy, int& cz) {
+  if (g.voxel_type == 0) {
+    double r = sqrt(x * x + y * y + z * z);
+    cx = (int)floor((atan2(y, x) + 3.14159265358979323846) / g.res[0]);
+    cy = (int)floor(acos(z / r) / g.res[1]);
+    cz = (int)floor(r / g.res[2]);
+  } else {
+    cx = (int)floor(x / g.res[0] - 0.5);
+    cy = (int)floor(y / g.res[1] - 0.5);
+    cz = (int)floor(z / g.res[2] - 0.5);
+  }
+}
+
+// Filtered path: evaluate in fp32 (polar) or with a reciprocal multiply (uniform), and only fall
+// back to the exact fp64 evaluation when the value lies within a conservative error bound of a cell
+// boundary. The returned coordinate always equals voxel_coord_exact().
+// Error budgets (absolute, before dividing by the resolution):
+//   theta: fp32 inputs (6e-8 rel) + atan2f (<=2 ulp of pi = 4.8e-7)      -> 1.5e-6 rad
+//   phi  : u = z/r (3e-7 abs) * 1/sqrt(1-u^2) (<= 2.3 for |u|<=0.9) + acosf (2 ulp) -> 4e-6 rad; |u|>0.9 -> exact
+//   r    : sqrtf chain 4e-7 relative
+__device__ __forceinline__ void voxel_coord(const GridParams& g, double x, double y, double z, int& cx, int& cy, int& cz) {
+  if (g.voxel_type == 0) {
+    const float xf = (float)x, yf = (float)y, zf = (float)z;
+    const float r2 = xf * xf + yf * yf + zf * zf;
+    const float rf = sqrtf(r2);
+    const float u = zf / rf;
+    const double th = ((double)atan2f(yf, xf) + 3.14159265358979323846) * g.inv_res[0];
+    const double ph = (double)acosf(u) * g.inv_res[1];
+    const double rr = (double)rf * g.inv_res[2];
+    const double fth = floor(th), fph = floor(ph), frr = floor(rr);
+    const double dth = 1.5e-6 * g.inv_res[0] + 1e-9 * th;
+    const double dph = 4.0e-6 * g.inv_res[1] + 1e-9 * ph;
+    const double drr = 4.0e-7 * rr + 1e-9;
+    bool safe = (th - fth > dth) && (fth + 1.0 - th > dth) && (ph - fph > dph) && (fph + 1.0 - ph > dph) &&
+                (rr - frr > drr) && (frr + 1.0 - rr > drr) && (fabsf(u) <= 0.9f) && (rf > 1e-3f) && (rf < 1e6f);
+    if (safe) { cx = (int)fth; cy = (int)fph; cz = (int)frr; }
+    else voxel_coord_exact(g, x, y, z, cx, cy, cz);
+  } else {
+    const double vx = x * g.inv_res[0] - 0.5, vy = y * g.inv_res[1] - 0.5, vz = z * g.inv_res[2] - 0.5;
+    const double fx = floor(vx), fy = floor(vy), fz = floor(vz);
+    const double ex = 1e-12 * (fabs(vx) + 1.0), ey = 1e-12 * (fabs(vy) + 1.0), ez = 1e-12 * (fabs(vz) + 1.0);
+    bool safe = (vx - fx > ex) && (fx + 1.0 - vx > ex) && (vy - fy > ey) && (fy + 1.0 - vy > ey) && (vz - fz > ez) && (fz + 1.0 - vz > ez);
+    if (safe) { cx = (int)fx; cy = (int)fy; cz = (int)fz; }
+    else voxel_coord_exact(g, x, y, z, cx, cy, cz);
+  }
+}
+
+// Hash lookup: returns compact voxel id or -1. Linear probing, table is read-only here.
+__device__ __forceinline__ int table_lookup(const VoxSlot* __restrict__ table, unsigned mask, int cx, int cy, int cz) {
+  if (!key_in_range(cx, cy, cz)) return -1;
+  const unsigned long long key = pack_key(cx, cy, cz);
+  unsigned h = hash_key(key) & mask;
+  #pragma unroll 1
+  for (unsigned probe = 0; probe <= mask; probe++) {
+    const ulonglong2 s = __ldg(reinterpret_cast<const ulonglong2*>(table + h));
+    if (s.x == key) return (int)(unsigned)(s.y & 0xFFFFFFFFull);
+    if (s.x == KEY_EMPTY) return -1;
+    h = (h + 1) & mask;
+  }
+  return -1;
+}
+#endif  // __CUDACC__
+
+}  // namespace rolo

@@ -1,0 +1,1074 @@
+// context.cu — registration context, device-memory pool, host drivers and the C-ABI (include/rolo_gicp.h).
+//
+// The product path is CUDA-only: every entry point fails with RG_ERR_NO_DEVICE / RG_ERR_CUDA when no
+// B200-class device is usable; there is no CPU fallback anywhere in this library.
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <chrono>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/rolo_gicp.h"
+#include "common.cuh"
+#include "covariance.cuh"
+#include "frontend.cuh"
+#include "linearize.cuh"
+#include "lsq_host.hpp"
+#include "voxelmap.cuh"
+
+using namespace rolo;
+
+namespace {
+
+std::mutex g_mutex;
+std::string g_last_error;
+std::atomic<unsigned> g_seq{0};   // launch sequence numbers written to the mapped completion flags
+
+// ------------------------------------------------------------------------------------------------
+// process-global caching pool: the caller constructs a fresh registration object every frame
+// (lidarOdometry.cpp:460), so device buffers, pinned blocks and streams must outlive contexts.
+// ------------------------------------------------------------------------------------------------
+struct Pool {
+  std::multimap<std::pair<int, size_t>, void*> free_dev;    // (device, bytes) -> ptr
+  std::multimap<size_t, void*> free_pinned;
+  std::multimap<int, cudaStream_t> free_streams;
+  std::map<void*, std::pair<int, size_t>> live_dev;
+  std::map<void*, size_t> live_pinned;
+
+  static size_t round_up(size_t b) {
+    size_t g = 256;
+    while (g < b) g <<= 1;
+    if (b > (size_t)1 << 20) { const size_t q = (size_t)1 << 20; g = (b + q - 1) / q * q; }
+    return g;
+  }
+  cudaError_t dev_alloc(int device, size_t bytes, void** out) {
+    bytes = round_up(std::max<size_t>(bytes, 256));
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto it = free_dev.find({device, bytes});
+    if (it != free_dev.end()) { *out = it->second; free_dev.erase(it); live_dev[*out] = {device, bytes}; return cudaSuccess; }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {   // release cached blocks and retry once
+      for (auto& kv : free_dev) cudaFree(kv.second);
+      free_dev.clear();
+      e = cudaMalloc(out, bytes);
+      if (e != cudaSuccess) return e;
+    }
+    live_dev[*out] = {device, bytes};
+    return cudaSuccess;
+  }
+  void dev_free(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto it = live_dev.find(p);
+    if (it == live_dev.end()) return;
+    free_dev.insert({it->second, p});
+    live_dev.erase(it);
+  }
+  cudaError_t pinned_alloc(size_t bytes, void** out) {
+    bytes = round_up(std::max<size_t>(bytes, 256));
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto it = free_pinned.find(bytes);
+    if (it != free_pinned.end()) { *out = it->second; free_pinned.erase(it); live_pinned[*out] = bytes; return cudaSuccess; }
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e != cudaSuccess) return e;
+    live_pinned[*out] = bytes;
+    return cudaSuccess;
+  }
+  void pinned_free(void* p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto it = live_pinned.find(p);
+    if (it == live_pinned.end()) return;
+    free_pinned.insert({it->second, p});
+    live_pinned.erase(it);
+  }
+  cudaError_t stream_get(int device, cudaStream_t* s) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto it = free_streams.find(device);
+    if (it != free_streams.end()) { *s = it->second; free_streams.erase(it); return cudaSuccess; }
+    return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
+  }
+  void stream_put(int device, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    free_streams.insert({device, s});
+  }
+};
+Pool& pool() { static Pool* p = new Pool; return *p; }   // intentionally leaked: safe at process exit
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr; size_t cap = 0; int device = 0;
+  cudaError_t ensure(int dev, size_t count) {
+    if (count <= cap && p) return cudaSuccess;
+    release();
+    device = dev;
+    void* q = nullptr;
+    cudaError_t e = pool().dev_alloc(dev, std::max<size_t>(count, 1) * sizeof(T), &q);
+    if (e != cudaSuccess) return e;
+    p = (T*)q; cap = count;
+    return cudaSuccess;
+  }
+  void release() { if (p) pool().dev_free(p); p = nullptr; cap = 0; }
+};
+
+__global__ void extract_points_kernel(const unsigned char* __restrict__ raw, size_t stride, int n, int n_pad, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
+  if (i < n) {
+    const float* s = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+    p.x = s[0]; p.y = s[1]; p.z = s[2];
+  }
+  out[i] = p;
+}
+__global__ void copy_points_kernel(const float4* __restrict__ in, int n, int n_pad, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
+  if (i < n) { p = in[i]; p.w = 1.f; }
+  out[i] = p;
+}
+__global__ void cov_from_double_kernel(const double* __restrict__ cov16, int n, int n_pad, float* __restrict__ cov6) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  const size_t base = (size_t)(i / TILE_PTS) * COV_PLANES * TILE_PTS + (i % TILE_PTS);
+  float v[6] = {0, 0, 0, 0, 0, 0};
+  if (i < n) {
+    const double* c = cov16 + (size_t)i * 16;
+    v[0] = (float)c[0]; v[1] = (float)c[1]; v[2] = (float)c[2]; v[3] = (float)c[5]; v[4] = (float)c[6]; v[5] = (float)c[10];
+  }
+  for (int t = 0; t < 6; t++) cov6[base + (size_t)t * TILE_PTS] = v[t];
+}
+__global__ void cov_to_double_kernel(const float* __restrict__ cov6, int n, double* __restrict__ cov16) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t base = (size_t)(i / TILE_PTS) * COV_PLANES * TILE_PTS + (i % TILE_PTS);
+  double v[6];
+  for (int t = 0; t < 6; t++) v[t] = (double)cov6[base + (size_t)t * TILE_PTS];
+  double* c = cov16 + (size_t)i * 16;
+  c[0] = v[0]; c[1] = v[1]; c[2] = v[2]; c[3] = 0;
+  c[4] = v[1]; c[5] = v[3]; c[6] = v[4]; c[7] = 0;
+  c[8] = v[2]; c[9] = v[4]; c[10] = v[5]; c[11] = 0;
+  c[12] = c[13] = c[14] = c[15] = 0;
+}
+__global__ void transform_points_kernel(const float4* __restrict__ in, int n, const float* __restrict__ T /*16*/, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = in[i];
+  float4 o;
+  o.x = T[0] * p.x + T[1] * p.y + T[2] * p.z + T[3];
+  o.y = T[4] * p.x + T[5] * p.y + T[6] * p.z + T[7];
+  o.z = T[8] * p.x + T[9] * p.y + T[10] * p.z + T[11];
+  o.w = 1.f;
+  out[i] = o;
+}
+__global__ void table_dump_kernel(const VoxSlot* __restrict__ table, unsigned cap, const VoxPayload* __restrict__ vox,
+                                  unsigned long long* __restrict__ keys, VoxPayload* __restrict__ out) {
+  const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cap) return;
+  const VoxSlot sl = table[s];
+  if (sl.key == KEY_EMPTY) return;
+  keys[sl.id] = sl.key;
+  out[sl.id] = vox[sl.id];
+}
+
+struct Cloud {
+  DevBuf<float4> pts;
+  DevBuf<float> cov6;
+  int n = 0, n_pad = 0;
+  bool has_cov = false;
+  const void* host_identity = nullptr;   // the reference compares cloud pointers (rot_vgicp_impl.hpp:113,134)
+  void clear() { n = 0; n_pad = 0; has_cov = false; host_identity = nullptr; }
+  void release() { pts.release(); cov6.release(); clear(); }
+};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+struct rg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  mutable std::string err;
+
+  // RotVGICP members (rot_vgicp_impl.hpp:20-39)
+  int k_correspondences = 20;
+  int regularization_method = RG_REG_PLANE;
+  double voxel_resolution = 1.0;
+  float lambda_ = 1.0f;
+  int search_method = RG_DIRECT1;
+  int voxel_mode = RG_ACC_ADDITIVE;
+  int voxel_type = RG_VOXEL_POLAR;
+  double polar_resolution[3] = {1.0, 0.0, 0.0};   // Vector3d::Identity() (reference quirk Q4: unusable until set)
+  int num_threads = 0;
+
+  host::LsqDriver lsq;
+
+  Cloud src, tgt;
+
+  // voxel map
+  DevBuf<VoxSlot> table; unsigned mask = 0;
+  DevBuf<VoxPayload> vox;
+  DevBuf<double> sums;
+  DevBuf<int> slot_of_point;
+  DevBuf<int> counters;
+  bool voxel_ok = false;
+  int n_vox = -1;
+
+  // covariance scratch
+  DevBuf<unsigned long long> codes_in, codes_out;
+  DevBuf<int> idx_in, idx_out, bbox;
+  DevBuf<float4> sorted;
+  DevBuf<unsigned char> cub_temp;
+
+  // linearize
+  DevBuf<int> corr; int corr_noff = 0;
+  DevBuf<double> partials;
+  DevBuf<unsigned> counter;
+  DevBuf<double> result_dev;
+  DevBuf<LinStatic> st_dev; bool st_ok = false;
+  double* result_host = nullptr;        // mapped pinned [RES_N] (owned; stand-alone contexts)
+  unsigned* flag_host = nullptr;        // mapped pinned
+  double* result_view = nullptr;        // where the kernel writes this pair's result (own block or the batch's)
+  unsigned* flag_view = nullptr;
+  int blocks_per_pair = 0;
+  double R_lin[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  bool have_corr = false;
+  size_t num_corr = 0;
+
+  DevBuf<unsigned char> staging;        // raw host cloud upload / misc
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool profile = false;
+  double last_kernel_us = -1.0;
+
+  rg_reduce_fn reduce_fn = nullptr; void* reduce_user = nullptr; int reduce_on_device = 0;
+
+  rg_batch* batch = nullptr;            // non-null when owned by a batch
+  int batch_index = 0;
+};
+
+struct rg_batch {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<rg_ctx*> pairs;
+  DevBuf<LinStatic> st_dev;
+  DevBuf<LinDyn> dyn_dev;
+  LinDyn* dyn_host = nullptr;           // pinned staging [P]
+  double* result_host = nullptr;        // mapped pinned [P][RES_N]
+  unsigned* flag_host = nullptr;        // mapped pinned [P]
+  std::vector<int> active;
+  DevBuf<LinStatic> st_sub; DevBuf<LinDyn> dyn_sub;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double lin_us_sum = 0; int lin_launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int set_err(const rg_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  { std::lock_guard<std::mutex> lk(g_mutex); g_last_error = msg; }
+  return code;
+}
+#define RG_CUDA(ctx, expr)                                                                          \
+  do {                                                                                              \
+    cudaError_t _e = (expr);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return set_err(ctx, RG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+  } while (0)
+
+int use_device(const rg_ctx* c) {
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) return set_err(c, RG_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  return RG_OK;
+}
+
+int noff_of(int method) { return method == RG_DIRECT1 ? 1 : (method == RG_DIRECT7 ? 7 : (method == RG_DIRECT27 ? 27 : 0)); }
+
+GridParams make_grid(const rg_ctx* c) {
+  GridParams g;
+  g.voxel_type = c->voxel_type;
+  for (int i = 0; i < 3; i++) {
+    g.res[i] = (c->voxel_type == RG_VOXEL_POLAR) ? c->polar_resolution[i] : c->voxel_resolution;
+    g.inv_res[i] = 1.0 / g.res[i];
+  }
+  return g;
+}
+
+int upload_cloud(rg_ctx* c, Cloud& cl, const float* host, size_t n, size_t stride_bytes) {
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (n > 0 && !host) return set_err(c, RG_ERR_INVALID, "null cloud pointer");
+  if (stride_bytes < 12 || stride_bytes % 4) return set_err(c, RG_ERR_INVALID, "stride_bytes must be a multiple of 4 and >= 12");
+  if (n > (size_t)1 << 30) return set_err(c, RG_ERR_INVALID, "cloud too large");
+  const int n_pad = (int)((n + TILE_PTS - 1) / TILE_PTS * TILE_PTS);
+  RG_CUDA(c, cl.pts.ensure(c->device, std::max(n_pad, TILE_PTS)));
+  RG_CUDA(c, cl.cov6.ensure(c->device, (size_t)std::max(n_pad, TILE_PTS) * COV_PLANES));
+  cl.n = (int)n; cl.n_pad = n_pad; cl.has_cov = false; cl.host_identity = host;
+  if (n == 0) return RG_OK;
+  RG_CUDA(c, c->staging.ensure(c->device, n * stride_bytes));
+  RG_CUDA(c, cudaMemcpyAsync(c->staging.p, host, n * stride_bytes, cudaMemcpyHostToDevice, c->stream));
+  extract_points_kernel<<<(n_pad + 255) / 256, 256, 0, c->stream>>>(c->staging.p, stride_bytes, (int)n, n_pad, cl.pts.p);
+  RG_CUDA(c, cudaGetLastError());
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));   // contract: the host buffer is consumed before returning
+  return RG_OK;
+}
+
+int upload_cloud_device(rg_ctx* c, Cloud& cl, const float* dev, size_t n, cudaStream_t user_stream) {
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (n > 0 && !dev) return set_err(c, RG_ERR_INVALID, "null cloud pointer");
+  const int n_pad = (int)((n + TILE_PTS - 1) / TILE_PTS * TILE_PTS);
+  RG_CUDA(c, cl.pts.ensure(c->device, std::max(n_pad, TILE_PTS)));
+  RG_CUDA(c, cl.cov6.ensure(c->device, (size_t)std::max(n_pad, TILE_PTS) * COV_PLANES));
+  cl.n = (int)n; cl.n_pad = n_pad; cl.has_cov = false; cl.host_identity = dev;
+  if (n == 0) return RG_OK;
+  if (user_stream && user_stream != c->stream) {   // order after the producer stream
+    cudaEvent_t ev;
+    RG_CUDA(c, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    cudaEventRecord(ev, user_stream);
+    cudaStreamWaitEvent(c->stream, ev, 0);
+    cudaEventDestroy(ev);
+  }
+  copy_points_kernel<<<(n_pad + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(dev), (int)n, n_pad, cl.pts.p);
+  RG_CUDA(c, cudaGetLastError());
+  return RG_OK;
+}
+
+int calc_cov(rg_ctx* c, Cloud& cl) {
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (cl.n == 0) return set_err(c, RG_ERR_INVALID, "calculate_covariances: empty cloud");
+  if (c->regularization_method < RG_REG_NONE || c->regularization_method > RG_REG_PLANE_S)
+    return set_err(c, RG_ERR_UNSUPPORTED, "here must not be reached (unknown regularization method; reference abort()s, rot_vgicp_impl.hpp:472-474)");
+  if (c->k_correspondences < 1 || c->k_correspondences > 64) return set_err(c, RG_ERR_INVALID, "k_correspondences must be in [1,64]");
+  if (cl.n < c->k_correspondences)
+    return set_err(c, RG_ERR_INVALID, "cloud has fewer points than k_correspondences (reference reads uninitialised neighbours here, rot_vgicp_impl.hpp:438-444)");
+  const int n = cl.n;
+  RG_CUDA(c, c->codes_in.ensure(c->device, n)); RG_CUDA(c, c->codes_out.ensure(c->device, n));
+  RG_CUDA(c, c->idx_in.ensure(c->device, n)); RG_CUDA(c, c->idx_out.ensure(c->device, n));
+  RG_CUDA(c, c->sorted.ensure(c->device, n)); RG_CUDA(c, c->bbox.ensure(c->device, 8));
+  const size_t tb = cov_cub_temp_bytes(n);
+  RG_CUDA(c, c->cub_temp.ensure(c->device, tb));
+  CovLaunch L;
+  L.pts = cl.pts.p; L.n = n; L.k = c->k_correspondences; L.method = c->regularization_method;
+  L.cov6 = cl.cov6.p; L.knn_out = nullptr;
+  L.s.codes_in = c->codes_in.p; L.s.codes_out = c->codes_out.p; L.s.idx_in = c->idx_in.p; L.s.idx_out = c->idx_out.p;
+  L.s.sorted = c->sorted.p; L.s.cub_temp = c->cub_temp.p; L.s.cub_temp_bytes = tb; L.s.bbox = c->bbox.p;
+  // zero the padding rows of the covariance tiles (only the last tile has any)
+  if (cl.n_pad > n) RG_CUDA(c, cudaMemsetAsync(cl.cov6.p + (size_t)(cl.n_pad / TILE_PTS - 1) * COV_PLANES * TILE_PTS, 0, sizeof(float) * COV_PLANES * TILE_PTS, c->stream));
+  RG_CUDA(c, launch_covariances(L, c->stream));
+  cl.has_cov = true;
+  return RG_OK;
+}
+
+int check_grid(rg_ctx* c) {
+  if (c->voxel_type == RG_VOXEL_POLAR) {
+    for (int i = 0; i < 3; i++)
+      if (!(c->polar_resolution[i] > 0.0))
+        return set_err(c, RG_ERR_INVALID, "polar resolution not set: call setPolarResolution/setResolution first (the reference default (1,0,0) divides by zero, rot_vgicp_impl.hpp:38, vmp_voxel.hpp:210)");
+  } else if (!(c->voxel_resolution > 0.0)) {
+    return set_err(c, RG_ERR_INVALID, "voxel resolution must be positive");
+  }
+  if (noff_of(c->search_method) == 0)
+    return set_err(c, RG_ERR_UNSUPPORTED, "unsupported neighbor search method (reference abort()s, vmp_voxel.hpp:16-18)");
+  return RG_OK;
+}
+
+int build_voxelmap(rg_ctx* c) {
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (int rc = check_grid(c)) return rc;
+  if (c->tgt.n == 0) return set_err(c, RG_ERR_INVALID, "create_voxelmap: no target cloud");
+  if (!c->tgt.has_cov) return set_err(c, RG_ERR_INVALID, "create_voxelmap: target covariances missing");
+  const int n = c->tgt.n;
+  size_t cap = 1024;
+  while (cap < (size_t)2 * n) cap <<= 1;
+  RG_CUDA(c, c->table.ensure(c->device, cap));
+  c->mask = (unsigned)(cap - 1);
+  RG_CUDA(c, c->vox.ensure(c->device, n));
+  RG_CUDA(c, c->sums.ensure(c->device, (size_t)n * 10));
+  RG_CUDA(c, c->slot_of_point.ensure(c->device, n));
+  RG_CUDA(c, c->counters.ensure(c->device, 2));
+  VoxelBuild b;
+  b.pts = c->tgt.pts.p; b.cov6 = c->tgt.cov6.p; b.n = n; b.grid = make_grid(c);
+  b.table = c->table.p; b.mask = c->mask; b.slot_of_point = c->slot_of_point.p; b.counters = c->counters.p;
+  b.sums = c->sums.p; b.vox = c->vox.p;
+  RG_CUDA(c, launch_voxel_build(b, c->stream));
+  c->voxel_ok = true; c->n_vox = -1; c->st_ok = false; c->have_corr = false;
+  return RG_OK;
+}
+
+int fetch_voxel_count(rg_ctx* c) {
+  if (!c->voxel_ok) return 0;
+  if (c->n_vox >= 0) return c->n_vox;
+  int h[2] = {0, 0};
+  if (cudaMemcpyAsync(h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+  if (h[1] != 0) { set_err(c, RG_ERR_INVALID, "voxel coordinate out of the +-2^20 key range (or table overflow)"); return -1; }
+  c->n_vox = h[0];
+  return c->n_vox;
+}
+
+int sm_count(int device) {
+  static std::map<int, int> cache;
+  std::lock_guard<std::mutex> lk(g_mutex);
+  auto it = cache.find(device);
+  if (it != cache.end()) return it->second;
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+  cache[device] = n;
+  return n;
+}
+
+int choose_blocks_per_pair(int device, int n, int n_pairs) {
+  const int ntiles = std::max(1, (n + TILE_PTS - 1) / TILE_PTS);
+  const int slots = sm_count(device) * 2;                     // 2 resident CTAs per SM (launch bounds)
+  int per_pair = std::max(1, (slots * 2 + n_pairs - 1) / n_pairs);   // ~2 waves of CTAs over the whole batch
+  if (n_pairs == 1) per_pair = slots;
+  return std::min(ntiles, per_pair);
+}
+
+// make sure the static descriptor + scratch for the fused kernel exist
+int prepare_linearize(rg_ctx* c) {
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (int rc = check_grid(c)) return rc;
+  if (c->src.n == 0) return set_err(c, RG_ERR_INVALID, "no source cloud");
+  if (!c->src.has_cov) return set_err(c, RG_ERR_INVALID, "source covariances missing");
+  if (!c->voxel_ok) { if (int rc = build_voxelmap(c)) return rc; }   // lazily, as rot_vgicp_impl.hpp:227-230
+  const int noff = noff_of(c->search_method);
+  if (c->st_ok && c->corr_noff == noff) return RG_OK;
+  const int n_pairs = c->batch ? (int)c->batch->pairs.size() : 1;
+  c->blocks_per_pair = choose_blocks_per_pair(c->device, c->src.n, n_pairs);
+  RG_CUDA(c, c->corr.ensure(c->device, (size_t)c->src.n * noff));
+  c->corr_noff = noff; c->have_corr = false;
+  RG_CUDA(c, c->partials.ensure(c->device, (size_t)c->blocks_per_pair * RES_N));
+  if (!c->counter.p) { RG_CUDA(c, c->counter.ensure(c->device, 4)); RG_CUDA(c, cudaMemsetAsync(c->counter.p, 0, 4 * sizeof(unsigned), c->stream)); }
+  RG_CUDA(c, c->result_dev.ensure(c->device, RES_N));
+  RG_CUDA(c, c->st_dev.ensure(c->device, 1));
+  if (!c->batch) {
+    if (!c->result_host) {
+      void* p = nullptr;
+      RG_CUDA(c, pool().pinned_alloc(RES_N * sizeof(double) + 64, &p));
+      c->result_host = (double*)p;
+      c->flag_host = (unsigned*)((char*)p + RES_N * sizeof(double));
+      *c->flag_host = 0;
+    }
+  }
+  LinStatic st;
+  st.src = c->src.pts.p; st.cov6 = c->src.cov6.p; st.n = c->src.n; st.mask = c->mask; st.table = c->table.p; st.vox = c->vox.p;
+  st.corr = c->corr.p; st.partials = c->partials.p; st.counter = c->counter.p;
+  const bool to_host = !c->batch && !(c->reduce_fn && c->reduce_on_device);
+  if (c->batch) { c->result_view = c->batch->result_host + (size_t)c->batch_index * RES_N; c->flag_view = c->batch->flag_host + c->batch_index; }
+  else { c->result_view = c->result_host; c->flag_view = c->flag_host; }
+  st.result = to_host || c->batch ? c->result_view : c->result_dev.p;
+  st.done_flag = to_host || c->batch ? c->flag_view : nullptr;
+  st.grid = make_grid(c);
+  RG_CUDA(c, cudaMemcpyAsync(c->st_dev.p, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+  if (c->batch) RG_CUDA(c, cudaMemcpyAsync(c->batch->st_dev.p + c->batch_index, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));   // `st` is a stack object
+  c->st_ok = true;
+  return RG_OK;
+}
+
+void fill_dyn_pose(LinDyn& d, const double* T, const double* Rm) {
+  for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) d.R[i * 3 + j] = T[i * 4 + j]; d.t[i] = T[i * 4 + 3]; }
+  for (int i = 0; i < 9; i++) d.Rm[i] = Rm[i];
+  d.ct[0] = d.ct[1] = d.ct[2] = 0.0; d.lam_c = 0.0; d.h_scale = 1.0; d.b_ct_scale = 0.0; d.pad = 0;
+}
+
+// Build the launch description of one evaluation request; returns mode/refresh.
+int make_dyn(rg_ctx* c, const host::Request& r, const double* t3_guess, const double* /*t3_last*/, double dtn, double dtn1,
+             LinDyn& d, int& mode, int& refresh) {
+  double T[16];
+  switch (r.kind) {
+    case host::REQ_LIN6:
+    case host::REQ_LIN3: {
+      double Rm[9];
+      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Rm[i * 3 + j] = r.pose[i * 4 + j];
+      fill_dyn_pose(d, r.pose, Rm);
+      std::memcpy(c->R_lin, Rm, sizeof(Rm));
+      mode = (r.kind == host::REQ_LIN6) ? LIN_SE3 : LIN_SO3; refresh = 1;
+      return RG_OK;
+    }
+    case host::REQ_ERROR:
+      if (!c->have_corr) return set_err(c, RG_ERR_INVALID, "compute_error before any linearize (no correspondences)");
+      fill_dyn_pose(d, r.pose, c->R_lin);
+      mode = LIN_COST; refresh = 0;
+      return RG_OK;
+    case host::REQ_T3_LIN:
+    case host::REQ_T_ERROR: {
+      if (!c->have_corr) return set_err(c, RG_ERR_INVALID, "translation stage before any linearize (no correspondences)");
+      host::mat4_identity(T);
+      T[3] = r.t[0]; T[7] = r.t[1]; T[11] = r.t[2];
+      fill_dyn_pose(d, T, c->R_lin);
+      // ct = ((p - g) - (p + t))/dtn - last_transform/dtn1 (rot_vgicp_impl.hpp:544-548 / 642-646).
+      // Reference quirk Q3: `last_transform.matrix().col(3).head<3>() = last_t0` indexes column 3 of a 4x1
+      // vector, so last_t0 never reaches last_transform: it stays Zero in t3_linearize (impl.hpp:539) and
+      // Vector4d::Identity() = (1,0,0,0) in compute_t_error (impl.hpp:637). Replicated.
+      const double lx = (r.kind == host::REQ_T_ERROR) ? 1.0 : 0.0;
+      d.ct[0] = -(t3_guess[0] + r.t[0]) / dtn - lx / dtn1;
+      d.ct[1] = -(t3_guess[1] + r.t[1]) / dtn;
+      d.ct[2] = -(t3_guess[2] + r.t[2]) / dtn;
+      const double pt_size = (double)c->num_corr;
+      d.lam_c = (double)c->lambda_ / pt_size;                                   // impl.hpp:555,582
+      d.h_scale = 1.0 + d.lam_c / (dtn * dtn);
+      d.b_ct_scale = d.lam_c / dtn;
+      mode = (r.kind == host::REQ_T3_LIN) ? LIN_SE3 : LIN_COST; refresh = 0;
+      return RG_OK;
+    }
+  }
+  return set_err(c, RG_ERR_INVALID, "bad request");
+}
+
+int wait_flag(rg_ctx* c, volatile unsigned* flag, unsigned seq, cudaStream_t stream) {
+  const auto t0 = std::chrono::steady_clock::now();
+  unsigned spins = 0;
+  while (*flag != seq) {
+    if ((++spins & 0x3FFF) == 0) {
+      cudaError_t q = cudaStreamQuery(stream);
+      if (q != cudaSuccess && q != cudaErrorNotReady) return set_err(c, RG_ERR_CUDA, std::string("kernel failed: ") + cudaGetErrorString(q));
+      if (q == cudaSuccess && *flag != seq) {
+        // stream drained but flag not set: give the mapped write a moment, then fail
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(2)) return set_err(c, RG_ERR_CUDA, "result flag never arrived");
+      }
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(60)) return set_err(c, RG_ERR_CUDA, "timeout waiting for the fused kernel");
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  return RG_OK;
+}
+
+// one evaluation on a stand-alone context; res receives RES_N doubles
+int evaluate_single(rg_ctx* c, const host::Request& r, const double* g3, const double* l3, double dtn, double dtn1, double* res) {
+  if (int rc = prepare_linearize(c)) return rc;
+  LinDyn d; int mode = 0, refresh = 0;
+  if (int rc = make_dyn(c, r, g3, l3, dtn, dtn1, d, mode, refresh)) return rc;
+  d.seq = ++g_seq;
+  LinLaunch L;
+  L.mode = mode; L.refresh = refresh; L.noff = c->corr_noff; L.n_pairs = 1; L.blocks_per_pair = c->blocks_per_pair;
+  L.st = c->st_dev.p; L.dyn = nullptr;
+  if (c->profile) cudaEventRecord(c->ev0, c->stream);
+  RG_CUDA(c, launch_linearize(L, &d, c->stream));
+  if (c->profile) cudaEventRecord(c->ev1, c->stream);
+  const bool on_dev = c->reduce_fn && c->reduce_on_device && !c->batch;
+  if (on_dev) {
+    if (int rc = c->reduce_fn(c->reduce_user, c->result_dev.p, RES_N, 1, (void*)c->stream)) return set_err(c, RG_ERR_CUDA, "reduce hook failed (" + std::to_string(rc) + ")");
+    RG_CUDA(c, cudaMemcpyAsync(res, c->result_dev.p, RES_N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  } else {
+    if (int rc = wait_flag(c, c->flag_view, d.seq, c->stream)) return rc;
+    std::memcpy(res, c->result_view, RES_N * sizeof(double));
+    if (c->reduce_fn) if (int rc = c->reduce_fn(c->reduce_user, res, RES_N, 0, nullptr)) return set_err(c, RG_ERR_CUDA, "reduce hook failed (" + std::to_string(rc) + ")");
+  }
+  if (c->profile) { cudaEventSynchronize(c->ev1); float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_kernel_us = ms * 1e3; }
+  if (refresh) { c->have_corr = true; c->num_corr = (size_t)(res[28] + 0.5); }
+  return RG_OK;
+}
+
+int ensure_covariances(rg_ctx* c) {
+  // rot_vgicp_impl.hpp:153-158: recompute when the stored count differs from the cloud size
+  if (!c->src.has_cov) { if (int rc = calc_cov(c, c->src)) return rc; }
+  if (!c->tgt.has_cov) { if (int rc = calc_cov(c, c->tgt)) return rc; }
+  return RG_OK;
+}
+
+int run_driver(rg_ctx* c, const double* g3, const double* l3, double dtn, double dtn1) {
+  host::Request r;
+  double res[RES_N], H[36], b[6], cost;
+  while (c->lsq.want(r)) {
+    if (int rc = evaluate_single(c, r, g3, l3, dtn, dtn1, res)) return rc;
+    const int ndof = (r.kind == host::REQ_LIN3) ? 3 : 6;
+    if (r.kind == host::REQ_ERROR || r.kind == host::REQ_T_ERROR) { cost = res[27]; c->lsq.feed(nullptr, nullptr, cost); }
+    else { unpack_result(res, ndof, H, b, &cost); c->lsq.feed(H, b, cost); }
+  }
+  return RG_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+int rg_abi_version(void) { return ROLO_GICP_ABI_VERSION; }
+
+int rg_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char* rg_last_error(const rg_ctx* ctx) {
+  if (ctx) return ctx->err.c_str();
+  static thread_local std::string copy;
+  std::lock_guard<std::mutex> lk(g_mutex);
+  copy = g_last_error;
+  return copy.c_str();
+}
+
+static int create_ctx(int device, cudaStream_t shared_stream, rg_ctx** out) {
+  if (!out) return set_err(nullptr, RG_ERR_INVALID, "rg_create: null out");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_err(nullptr, RG_ERR_NO_DEVICE, "no CUDA device: the B200 core has no CPU fallback");
+  }
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) device = 0; }
+  if (device >= ndev) return set_err(nullptr, RG_ERR_INVALID, "device index out of range");
+  if ((e = cudaSetDevice(device)) != cudaSuccess) return set_err(nullptr, RG_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  rg_ctx* c = new rg_ctx;
+  c->device = device;
+  if (shared_stream) { c->stream = shared_stream; c->own_stream = false; }
+  else if ((e = pool().stream_get(device, &c->stream)) != cudaSuccess) { delete c; return set_err(nullptr, RG_ERR_CUDA, std::string("stream: ") + cudaGetErrorString(e)); }
+  cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+  *out = c;
+  return RG_OK;
+}
+
+int rg_create(int device, rg_ctx** out) { return create_ctx(device, nullptr, out); }
+
+void rg_destroy(rg_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  c->src.release(); c->tgt.release();
+  c->table.release(); c->vox.release(); c->sums.release(); c->slot_of_point.release(); c->counters.release();
+  c->codes_in.release(); c->codes_out.release(); c->idx_in.release(); c->idx_out.release(); c->bbox.release(); c->sorted.release(); c->cub_temp.release();
+  c->corr.release(); c->partials.release(); c->counter.release(); c->result_dev.release(); c->st_dev.release(); c->staging.release();
+  if (c->result_host) pool().pinned_free(c->result_host);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->own_stream && c->stream) pool().stream_put(c->device, c->stream);
+  delete c;
+}
+
+#define CHECK_CTX(c) do { if (!(c)) return set_err(nullptr, RG_ERR_INVALID, "null context"); } while (0)
+
+int rg_set_resolution(rg_ctx* c, double r) { CHECK_CTX(c); c->voxel_resolution = r; c->voxel_type = RG_VOXEL_UNIFORM; c->voxel_ok = false; c->st_ok = false; return RG_OK; }
+int rg_set_polar_resolution(rg_ctx* c, double th, double ph, double r) {
+  CHECK_CTX(c); c->polar_resolution[0] = th; c->polar_resolution[1] = ph; c->polar_resolution[2] = r; c->voxel_type = RG_VOXEL_POLAR; c->voxel_ok = false; c->st_ok = false; return RG_OK;
+}
+int rg_set_voxel_accumulation_mode(rg_ctx* c, int m) {
+  CHECK_CTX(c);
+  if (m < RG_ACC_ADDITIVE || m > RG_ACC_MULTIPLICATIVE) return set_err(c, RG_ERR_INVALID, "bad accumulation mode");
+  c->voxel_mode = m;   // all three modes use the additive voxel in the reference (vmp_voxel.hpp:176-185, quirk Q6)
+  return RG_OK;
+}
+int rg_set_neighbor_search_method(rg_ctx* c, int m) { CHECK_CTX(c); c->search_method = m; c->st_ok = false; return RG_OK; }
+int rg_set_num_threads(rg_ctx* c, int n) { CHECK_CTX(c); c->num_threads = n; return RG_OK; }
+int rg_set_correspondence_randomness(rg_ctx* c, int k) { CHECK_CTX(c); c->k_correspondences = k; return RG_OK; }
+int rg_set_regularization_method(rg_ctx* c, int m) { CHECK_CTX(c); c->regularization_method = m; return RG_OK; }
+int rg_set_optimizer_type(rg_ctx* c, int t) {
+  CHECK_CTX(c);
+  if (t < RG_OPT_GAUSS_NEWTON || t > RG_OPT_SO3_LM) t = RG_OPT_LM;   // lsq.hpp:204 default branch
+  c->lsq.cfg.optimizer = t; return RG_OK;
+}
+int rg_set_rotation_epsilon(rg_ctx* c, double e) { CHECK_CTX(c); c->lsq.cfg.rotation_epsilon = e; return RG_OK; }
+int rg_set_transformation_epsilon(rg_ctx* c, double e) { CHECK_CTX(c); c->lsq.cfg.transformation_epsilon = e; return RG_OK; }
+int rg_set_maximum_iterations(rg_ctx* c, int n) { CHECK_CTX(c); c->lsq.cfg.max_iterations = n; return RG_OK; }
+int rg_set_initial_lambda_factor(rg_ctx* c, double f) { CHECK_CTX(c); c->lsq.cfg.lm_init_lambda_factor = f; return RG_OK; }
+int rg_set_debug_print(rg_ctx* c, int on) { CHECK_CTX(c); c->lsq.cfg.debug_print = on != 0; return RG_OK; }
+int rg_set_ct_lambda(rg_ctx* c, float l) { CHECK_CTX(c); c->lambda_ = l; return RG_OK; }
+int rg_set_profile(rg_ctx* c, int on) { CHECK_CTX(c); c->profile = on != 0; return RG_OK; }
+double rg_last_kernel_us(const rg_ctx* c) { return c ? c->last_kernel_us : -1.0; }
+
+int rg_set_input_source(rg_ctx* c, const float* pts, size_t n, size_t stride) {
+  CHECK_CTX(c);
+  int rc = upload_cloud(c, c->src, pts, n, stride);
+  c->st_ok = false; c->have_corr = false;
+  return rc;
+}
+int rg_set_input_target(rg_ctx* c, const float* pts, size_t n, size_t stride) {
+  CHECK_CTX(c);
+  int rc = upload_cloud(c, c->tgt, pts, n, stride);
+  c->voxel_ok = false; c->st_ok = false; c->have_corr = false;
+  return rc;
+}
+int rg_set_input_source_device(rg_ctx* c, const float* dev, size_t n, void* stream) {
+  CHECK_CTX(c);
+  int rc = upload_cloud_device(c, c->src, dev, n, (cudaStream_t)stream);
+  c->st_ok = false; c->have_corr = false;
+  return rc;
+}
+int rg_set_input_target_device(rg_ctx* c, const float* dev, size_t n, void* stream) {
+  CHECK_CTX(c);
+  int rc = upload_cloud_device(c, c->tgt, dev, n, (cudaStream_t)stream);
+  c->voxel_ok = false; c->st_ok = false; c->have_corr = false;
+  return rc;
+}
+int rg_clear_source(rg_ctx* c) { CHECK_CTX(c); c->src.clear(); c->st_ok = false; c->have_corr = false; return RG_OK; }
+int rg_clear_target(rg_ctx* c) { CHECK_CTX(c); c->tgt.clear(); c->voxel_ok = false; c->st_ok = false; c->have_corr = false; return RG_OK; }
+int rg_swap_source_and_target(rg_ctx* c) {
+  CHECK_CTX(c);
+  std::swap(c->src, c->tgt);
+  c->voxel_ok = false; c->st_ok = false; c->have_corr = false; c->num_corr = 0;
+  return RG_OK;
+}
+size_t rg_source_size(const rg_ctx* c) { return c ? (size_t)c->src.n : 0; }
+size_t rg_target_size(const rg_ctx* c) { return c ? (size_t)c->tgt.n : 0; }
+
+int rg_set_covariances(rg_ctx* c, int which, const double* cov, size_t n) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  Cloud& cl = which == RG_SOURCE ? c->src : c->tgt;
+  if (n != (size_t)cl.n) {
+    // the reference stores any vector and recomputes at align() when the size mismatches (rot_vgicp_impl.hpp:153-158)
+    cl.has_cov = false;
+    return RG_OK;
+  }
+  if (n == 0) return RG_OK;
+  if (!cov) return set_err(c, RG_ERR_INVALID, "null covariance pointer");
+  RG_CUDA(c, c->staging.ensure(c->device, n * 16 * sizeof(double)));
+  RG_CUDA(c, cudaMemcpyAsync(c->staging.p, cov, n * 16 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  cov_from_double_kernel<<<(cl.n_pad + 255) / 256, 256, 0, c->stream>>>((const double*)c->staging.p, cl.n, cl.n_pad, cl.cov6.p);
+  RG_CUDA(c, cudaGetLastError());
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  cl.has_cov = true;
+  if (which == RG_TARGET) { c->voxel_ok = false; c->st_ok = false; }
+  return RG_OK;
+}
+
+size_t rg_get_covariances(rg_ctx* c, int which, double* out) {
+  if (!c) return 0;
+  Cloud& cl = which == RG_SOURCE ? c->src : c->tgt;
+  if (!cl.has_cov) return 0;
+  if (!out) return (size_t)cl.n;
+  if (use_device(c)) return 0;
+  if (c->staging.ensure(c->device, (size_t)cl.n * 16 * sizeof(double)) != cudaSuccess) return 0;
+  cov_to_double_kernel<<<(cl.n + 255) / 256, 256, 0, c->stream>>>(cl.cov6.p, cl.n, (double*)c->staging.p);
+  if (cudaMemcpyAsync(out, c->staging.p, (size_t)cl.n * 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) return 0;
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return 0;
+  return (size_t)cl.n;
+}
+
+int rg_calculate_covariances(rg_ctx* c, int which) {
+  CHECK_CTX(c);
+  int rc = calc_cov(c, which == RG_SOURCE ? c->src : c->tgt);
+  if (rc == RG_OK && which == RG_TARGET) { c->voxel_ok = false; c->st_ok = false; }
+  return rc;
+}
+
+int rg_create_voxelmap(rg_ctx* c) {
+  CHECK_CTX(c);
+  if (!c->tgt.has_cov) { if (int rc = calc_cov(c, c->tgt)) return rc; }
+  if (int rc = build_voxelmap(c)) return rc;
+  return fetch_voxel_count(c) < 0 ? RG_ERR_INVALID : RG_OK;
+}
+
+static int eval_pose(rg_ctx* c, int kind, const double T[16], double* H, double* b, double* cost, int ndof) {
+  CHECK_CTX(c);
+  if (!T) return set_err(c, RG_ERR_INVALID, "null pose");
+  host::Request r; r.kind = kind; std::memcpy(r.pose, T, sizeof(r.pose));
+  double res[RES_N];
+  if (kind != host::REQ_ERROR) { if (int rc = ensure_covariances(c)) return rc; }
+  if (int rc = evaluate_single(c, r, nullptr, nullptr, 0, 0, res)) return rc;
+  unpack_result(res, ndof, H, b, cost);
+  return RG_OK;
+}
+int rg_linearize(rg_ctx* c, const double T[16], double* H, double* b, double* cost) { return eval_pose(c, host::REQ_LIN6, T, H, b, cost, 6); }
+int rg_so3_linearize(rg_ctx* c, const double T[16], double* H, double* b, double* cost) { return eval_pose(c, host::REQ_LIN3, T, H, b, cost, 3); }
+int rg_compute_error(rg_ctx* c, const double T[16], double* cost) { return eval_pose(c, host::REQ_ERROR, T, nullptr, nullptr, cost, 6); }
+
+int rg_t3_linearize(rg_ctx* c, const double t[3], const double g[3], const double l[3], double dtn, double dtn1, double* H, double* b, double* cost) {
+  CHECK_CTX(c);
+  host::Request r; r.kind = host::REQ_T3_LIN; std::memcpy(r.t, t, sizeof(r.t));
+  double res[RES_N];
+  if (int rc = evaluate_single(c, r, g, l, dtn, dtn1, res)) return rc;
+  unpack_result(res, 6, H, b, cost);
+  return RG_OK;
+}
+int rg_compute_t_error(rg_ctx* c, const double t[3], const double g[3], const double l[3], double dtn, double dtn1, double* cost) {
+  CHECK_CTX(c);
+  host::Request r; r.kind = host::REQ_T_ERROR; std::memcpy(r.t, t, sizeof(r.t));
+  double res[RES_N];
+  if (int rc = evaluate_single(c, r, g, l, dtn, dtn1, res)) return rc;
+  if (cost) *cost = res[27];
+  return RG_OK;
+}
+size_t rg_num_correspondences(const rg_ctx* c) { return c ? c->num_corr : 0; }
+
+int rg_align(rg_ctx* c, const float guess[16], float out_T[16]) {
+  CHECK_CTX(c);
+  if (!out_T) return set_err(c, RG_ERR_INVALID, "null output");
+  if (c->src.n == 0 || c->tgt.n == 0) return set_err(c, RG_ERR_INVALID, "align: source/target cloud not set");
+  c->voxel_ok = false; c->st_ok = false; c->have_corr = false;      // voxelmap_.reset() (rot_vgicp_impl.hpp:147)
+  if (int rc = check_grid(c)) return rc;
+  if (int rc = ensure_covariances(c)) return rc;
+  double g[16];
+  if (guess) for (int i = 0; i < 16; i++) g[i] = (double)guess[i]; else host::mat4_identity(g);
+  c->lsq.begin_align(g);
+  if (int rc = run_driver(c, nullptr, nullptr, 0, 0)) return rc;
+  for (int i = 0; i < 16; i++) out_T[i] = (float)c->lsq.x0[i];      // final_transformation_ = x0.cast<float>() (lsq.hpp:177)
+  return c->lsq.failed ? RG_ERR_NOT_CONVERGED : RG_OK;
+}
+
+int rg_compute_translation(rg_ctx* c, double trans[3], const double g[3], const double l[3], double dtn, double dtn1, float ct_lambda) {
+  CHECK_CTX(c);
+  if (!trans || !g || !l) return set_err(c, RG_ERR_INVALID, "null argument");
+  c->lambda_ = ct_lambda;                                           // rot_vgicp_impl.hpp:166
+  c->lsq.begin_translation(trans);
+  if (int rc = run_driver(c, g, l, dtn, dtn1)) return rc;
+  trans[0] = c->lsq.t0[0]; trans[1] = c->lsq.t0[1]; trans[2] = c->lsq.t0[2];
+  return c->lsq.failed ? RG_ERR_NOT_CONVERGED : RG_OK;
+}
+
+int rg_transform_source(rg_ctx* c, const float T[16], float* out, size_t stride) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  const int n = c->src.n;
+  if (n == 0) return RG_OK;
+  if (!out || !T || stride < 12 || stride % 4) return set_err(c, RG_ERR_INVALID, "bad arguments");
+  RG_CUDA(c, c->staging.ensure(c->device, (size_t)n * sizeof(float4) + 64));
+  float* dT = (float*)c->staging.p;
+  float4* dout = (float4*)((char*)c->staging.p + 64);
+  RG_CUDA(c, cudaMemcpyAsync(dT, T, 16 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  transform_points_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(c->src.pts.p, n, dT, dout);
+  RG_CUDA(c, cudaGetLastError());
+  std::vector<float4> tmp((size_t)n);
+  RG_CUDA(c, cudaMemcpyAsync(tmp.data(), dout, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < n; i++) {
+    float* o = (float*)((char*)out + (size_t)i * stride);
+    o[0] = tmp[i].x; o[1] = tmp[i].y; o[2] = tmp[i].z;
+  }
+  return RG_OK;
+}
+
+int rg_has_converged(const rg_ctx* c) { return c && c->lsq.converged ? 1 : 0; }
+int rg_nr_iterations(const rg_ctx* c) { return c ? c->lsq.nr_iterations : 0; }
+int rg_get_final_hessian(const rg_ctx* c, double H[36]) { CHECK_CTX(c); std::memcpy(H, c->lsq.final_hessian, sizeof(double) * 36); return RG_OK; }
+int rg_get_final_pose(const rg_ctx* c, double T[16]) { CHECK_CTX(c); std::memcpy(T, c->lsq.x0, sizeof(double) * 16); return RG_OK; }
+
+size_t rg_voxel_count(const rg_ctx* c) { int v = fetch_voxel_count(const_cast<rg_ctx*>(c)); return v < 0 ? 0 : (size_t)v; }
+
+int rg_get_voxels(rg_ctx* c, int32_t* keys, double* mean, double* cov6, int32_t* npts) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  const int V = fetch_voxel_count(c);
+  if (V < 0) return RG_ERR_INVALID;
+  if (V == 0) return RG_OK;
+  DevBuf<unsigned long long> dk; DevBuf<VoxPayload> dp;
+  RG_CUDA(c, dk.ensure(c->device, V)); RG_CUDA(c, dp.ensure(c->device, V));
+  const unsigned cap = c->mask + 1;
+  table_dump_kernel<<<(cap + 255) / 256, 256, 0, c->stream>>>(c->table.p, cap, c->vox.p, dk.p, dp.p);
+  std::vector<unsigned long long> hk(V); std::vector<VoxPayload> hp(V);
+  RG_CUDA(c, cudaMemcpyAsync(hk.data(), dk.p, sizeof(unsigned long long) * V, cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaMemcpyAsync(hp.data(), dp.p, sizeof(VoxPayload) * V, cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  dk.release(); dp.release();
+  std::vector<int> order(V);
+  std::vector<int> kx(V), ky(V), kz(V);
+  for (int i = 0; i < V; i++) { order[i] = i; unpack_key(hk[i], kx[i], ky[i], kz[i]); }
+  std::sort(order.begin(), order.end(), [&](int a, int b) {
+    if (kx[a] != kx[b]) return kx[a] < kx[b];
+    if (ky[a] != ky[b]) return ky[a] < ky[b];
+    return kz[a] < kz[b]; });
+  for (int o = 0; o < V; o++) {
+    const int i = order[o];
+    if (keys) { keys[o * 3 + 0] = kx[i]; keys[o * 3 + 1] = ky[i]; keys[o * 3 + 2] = kz[i]; }
+    if (mean) { mean[o * 3 + 0] = hp[i].mean[0]; mean[o * 3 + 1] = hp[i].mean[1]; mean[o * 3 + 2] = hp[i].mean[2]; }
+    if (cov6) for (int t = 0; t < 6; t++) cov6[o * 6 + t] = hp[i].cov[t];
+    if (npts) npts[o] = (int32_t)(hp[i].w * hp[i].w + 0.5);
+  }
+  return RG_OK;
+}
+
+int rg_get_correspondence_keys(rg_ctx* c, int32_t* keys) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (!c->have_corr) return set_err(c, RG_ERR_INVALID, "no correspondences yet");
+  const int V = fetch_voxel_count(c);
+  if (V < 0) return RG_ERR_INVALID;
+  const size_t m = (size_t)c->src.n * c->corr_noff;
+  std::vector<int> hc(m);
+  RG_CUDA(c, cudaMemcpyAsync(hc.data(), c->corr.p, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
+  std::vector<VoxSlot> ht((size_t)c->mask + 1);
+  RG_CUDA(c, cudaMemcpyAsync(ht.data(), c->table.p, sizeof(VoxSlot) * ht.size(), cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<unsigned long long> id2key(std::max(V, 1));
+  for (auto& s : ht) if (s.key != KEY_EMPTY && s.id >= 0 && s.id < V) id2key[s.id] = s.key;
+  for (size_t i = 0; i < m; i++) {
+    if (hc[i] < 0) { keys[i * 3] = keys[i * 3 + 1] = keys[i * 3 + 2] = INT32_MIN; continue; }
+    int x, y, z; unpack_key(id2key[hc[i]], x, y, z);
+    keys[i * 3] = x; keys[i * 3 + 1] = y; keys[i * 3 + 2] = z;
+  }
+  return RG_OK;
+}
+
+int rg_knn(rg_ctx* c, int which, int k, int32_t* out) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  Cloud& cl = which == RG_SOURCE ? c->src : c->tgt;
+  const int n = cl.n;
+  if (n == 0 || k < 1 || k > 64 || n < k || !out) return set_err(c, RG_ERR_INVALID, "rg_knn: bad arguments");
+  RG_CUDA(c, c->codes_in.ensure(c->device, n)); RG_CUDA(c, c->codes_out.ensure(c->device, n));
+  RG_CUDA(c, c->idx_in.ensure(c->device, n)); RG_CUDA(c, c->idx_out.ensure(c->device, n));
+  RG_CUDA(c, c->sorted.ensure(c->device, n)); RG_CUDA(c, c->bbox.ensure(c->device, 8));
+  const size_t tb = cov_cub_temp_bytes(n);
+  RG_CUDA(c, c->cub_temp.ensure(c->device, tb));
+  DevBuf<int> dk;
+  RG_CUDA(c, dk.ensure(c->device, (size_t)n * k));
+  CovLaunch L;
+  L.pts = cl.pts.p; L.n = n; L.k = k; L.method = c->regularization_method; L.cov6 = nullptr; L.knn_out = dk.p;
+  L.s.codes_in = c->codes_in.p; L.s.codes_out = c->codes_out.p; L.s.idx_in = c->idx_in.p; L.s.idx_out = c->idx_out.p;
+  L.s.sorted = c->sorted.p; L.s.cub_temp = c->cub_temp.p; L.s.cub_temp_bytes = tb; L.s.bbox = c->bbox.p;
+  RG_CUDA(c, launch_covariances(L, c->stream));
+  RG_CUDA(c, cudaMemcpyAsync(out, dk.p, sizeof(int) * (size_t)n * k, cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  dk.release();
+  return RG_OK;
+}
+
+int rg_set_reduce_hook(rg_ctx* c, rg_reduce_fn fn, void* user, int on_device) {
+  CHECK_CTX(c);
+  c->reduce_fn = fn; c->reduce_user = user; c->reduce_on_device = on_device; c->st_ok = false;
+  return RG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch of independent scan pairs
+// ------------------------------------------------------------------------------------------------
+int rg_batch_create(int device, int n_pairs, rg_batch** out) {
+  if (!out || n_pairs < 1) return set_err(nullptr, RG_ERR_INVALID, "rg_batch_create: bad arguments");
+  *out = nullptr;
+  rg_ctx* first = nullptr;
+  if (int rc = create_ctx(device, nullptr, &first)) return rc;
+  rg_batch* b = new rg_batch;
+  b->device = first->device;
+  b->stream = first->stream;          // the batch owns the stream through pair 0
+  first->batch = b; first->batch_index = 0;
+  b->pairs.push_back(first);
+  for (int i = 1; i < n_pairs; i++) {
+    rg_ctx* c = nullptr;
+    if (int rc = create_ctx(b->device, b->stream, &c)) { rg_batch_destroy(b); return rc; }
+    c->batch = b; c->batch_index = i;
+    b->pairs.push_back(c);
+  }
+  void* p = nullptr;
+  bool ok = b->st_dev.ensure(b->device, n_pairs) == cudaSuccess && b->dyn_dev.ensure(b->device, n_pairs) == cudaSuccess &&
+            b->st_sub.ensure(b->device, n_pairs) == cudaSuccess && b->dyn_sub.ensure(b->device, n_pairs) == cudaSuccess;
+  if (ok && pool().pinned_alloc(sizeof(LinDyn) * n_pairs, &p) == cudaSuccess) b->dyn_host = (LinDyn*)p; else ok = false;
+  if (ok && pool().pinned_alloc(sizeof(double) * RES_N * n_pairs, &p) == cudaSuccess) b->result_host = (double*)p; else ok = false;
+  if (ok && pool().pinned_alloc(sizeof(unsigned) * n_pairs + 64, &p) == cudaSuccess) b->flag_host = (unsigned*)p; else ok = false;
+  if (!ok) { rg_batch_destroy(b); return set_err(nullptr, RG_ERR_CUDA, "rg_batch_create: allocation failed"); }
+  std::memset(b->flag_host, 0, sizeof(unsigned) * n_pairs);
+  cudaEventCreate(&b->ev0); cudaEventCreate(&b->ev1);
+  *out = b;
+  return RG_OK;
+}
+
+void rg_batch_destroy(rg_batch* b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (size_t i = b->pairs.size(); i-- > 0;) rg_destroy(b->pairs[i]);   // pair 0 (stream owner) last
+  b->st_dev.release(); b->dyn_dev.release(); b->st_sub.release(); b->dyn_sub.release();
+  if (b->dyn_host) pool().pinned_free(b->dyn_host);
+  if (b->result_host) pool().pinned_free(b->result_host);
+  if (b->flag_host) pool().pinned_free(b->flag_host);
+  if (b->ev0) cudaEventDestroy(b->ev0);
+  if (b->ev1) cudaEventDestroy(b->ev1);
+  delete b;
+}
+
+rg_ctx* rg_batch_ctx(rg_batch* b, int pair) { return (b && pair >= 0 && pair < (int)b->pairs.size()) ? b->pairs[pair] : nullptr; }
+double rg_batch_last_linearize_us(const rg_batch* b) { return (b && b->lin_launches) ? b->lin_us_sum / b->lin_launches : -1.0; }
+int rg_batch_last_linearize_launches(const rg_batch* b) { return b ? b->lin_launches : 0; }
+
+int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
+  if (!b || !out_T) return set_err(nullptr, RG_ERR_INVALID, "rg_batch_align: bad arguments");
+  const int P = (int)b->pairs.size();
+  if (cudaSetDevice(b->device) != cudaSuccess) return set_err(nullptr, RG_ERR_CUDA, "cudaSetDevice failed");
+  // stage 1+2: covariances and voxel maps of every pair (stream-ordered, no host sync in between)
+  int noff = -1, bpp = -1;
+  for (int i = 0; i < P; i++) {
+    rg_ctx* c = b->pairs[i];
+    if (c->src.n == 0 || c->tgt.n == 0) return set_err(c, RG_ERR_INVALID, "batch align: source/target cloud not set");
+    c->voxel_ok = false; c->st_ok = false; c->have_corr = false;
+    if (int rc = check_grid(c)) return rc;
+    if (int rc = ensure_covariances(c)) return rc;
+    if (int rc = build_voxelmap(c)) return rc;
+  }
+  for (int i = 0; i < P; i++) {
+    rg_ctx* c = b->pairs[i];
+    if (int rc = prepare_linearize(c)) return rc;
+    if (noff < 0) { noff = c->corr_noff; bpp = c->blocks_per_pair; }
+    if (c->corr_noff != noff) return set_err(c, RG_ERR_INVALID, "batch align: all pairs must use the same neighbor search method");
+    bpp = std::min(bpp, c->blocks_per_pair);
+    double g[16];
+    if (guesses) for (int k = 0; k < 16; k++) g[k] = (double)guesses[i * 16 + k]; else host::mat4_identity(g);
+    c->lsq.begin_align(g);
+  }
+  b->lin_us_sum = 0; b->lin_launches = 0;
+  std::vector<host::Request> req(P);
+  std::vector<int> group;
+  std::vector<LinStatic> st_host(P);
+  RG_CUDA(nullptr, cudaMemcpyAsync(st_host.data(), b->st_dev.p, sizeof(LinStatic) * P, cudaMemcpyDeviceToHost, b->stream));
+  RG_CUDA(nullptr, cudaStreamSynchronize(b->stream));
+  for (;;) {
+    // collect the pending request of every unfinished pair and serve them grouped by kernel variant
+    std::vector<int> pend;
+    for (int i = 0; i < P; i++) if (b->pairs[i]->lsq.want(req[i])) pend.push_back(i);
+    if (pend.empty()) break;
+    for (int variant = 0; variant < 3; variant++) {
+      const int kind = variant == 0 ? host::REQ_LIN6 : (variant == 1 ? host::REQ_LIN3 : host::REQ_ERROR);
+      group.clear();
+      for (int i : pend) if (req[i].kind == kind) group.push_back(i);
+      if (group.empty()) continue;
+      const int G = (int)group.size();
+      int mode = 0, refresh = 0;
+      const unsigned seq = ++g_seq;
+      for (int gi = 0; gi < G; gi++) {
+        rg_ctx* c = b->pairs[group[gi]];
+        if (int rc = make_dyn(c, req[group[gi]], nullptr, nullptr, 0, 0, b->dyn_host[gi], mode, refresh)) return rc;
+        b->dyn_host[gi].seq = seq;
+      }
+      const LinStatic* st_arr = b->st_dev.p;
+      if (G != P) {   // compact the static descriptors of the active subset
+        std::vector<LinStatic> sub(G);
+        for (int gi = 0; gi < G; gi++) sub[gi] = st_host[group[gi]];
+        RG_CUDA(nullptr, cudaMemcpyAsync(b->st_sub.p, sub.data(), sizeof(LinStatic) * G, cudaMemcpyHostToDevice, b->stream));
+        RG_CUDA(nullptr, cudaStreamSynchronize(b->stream));
+        st_arr = b->st_sub.p;
+      }
+      RG_CUDA(nullptr, cudaMemcpyAsync(b->dyn_dev.p, b->dyn_host, sizeof(LinDyn) * G, cudaMemcpyHostToDevice, b->stream));
+      LinLaunch L;
+      L.mode = mode; L.refresh = refresh; L.noff = noff; L.n_pairs = G; L.blocks_per_pair = bpp; L.st = st_arr; L.dyn = b->dyn_dev.p;
+      cudaEventRecord(b->ev0, b->stream);
+      RG_CUDA(nullptr, launch_linearize(L, nullptr, b->stream));
+      cudaEventRecord(b->ev1, b->stream);
+      for (int gi = 0; gi < G; gi++) {
+        rg_ctx* c = b->pairs[group[gi]];
+        if (int rc = wait_flag(c, b->flag_host + group[gi], seq, b->stream)) return rc;
+      }
+      if (cudaEventSynchronize(b->ev1) == cudaSuccess) { float ms = 0; cudaEventElapsedTime(&ms, b->ev0, b->ev1); b->lin_us_sum += ms * 1e3; b->lin_launches++; }
+      for (int gi = 0; gi < G; gi++) {
+        const int i = group[gi];
+        rg_ctx* c = b->pairs[i];
+        const double* res = b->result_host + (size_t)i * RES_N;
+        double H[36], bb[6], cost;
+        if (kind == host::REQ_ERROR) c->lsq.feed(nullptr, nullptr, res[27]);
+        else {
+          c->have_corr = true; c->num_corr = (size_t)(res[28] + 0.5);
+          unpack_result(res, kind == host::REQ_LIN3 ? 3 : 6, H, bb, &cost);
+          c->lsq.feed(H, bb, cost);
+        }
+      }
+    }
+  }
+  int rc_all = RG_OK;
+  for (int i = 0; i < P; i++) {
+    rg_ctx* c = b->pairs[i];
+    for (int k = 0; k < 16; k++) out_T[i * 16 + k] = (float)c->lsq.x0[k];
+    if (c->lsq.failed) rc_all = RG_ERR_NOT_CONVERGED;
+  }
+  return rc_all;
+}
+
+}  // extern "C"

@@ -1,0 +1,376 @@
+// covariance.cu — RotVGICP::calculate_covariances on the GPU (rot_vgicp_impl.hpp:421-496).
+//
+// Reference: per point, pcl::search::KdTree::nearestKSearch(k=20) (FLANN, float L2), mean-centre the
+// 4 x k neighbour matrix, cov = N N^T / k, regularise through JacobiSVD (PLANE: U diag(1,1,1e-3) V^T).
+// Here (exact, no approximation of the neighbour set):
+//   1. bounding box, 63-bit Morton codes (21 bits/axis), radix sort of (code, index)  [cub::DeviceRadixSort
+//      is the only library call: plumbing, not the hot op]
+//   2. one thread per query walks an implicit octree over the sorted codes: at level L the 3x3x3 block
+//      of level-L cells around the query is scanned (each cell = one contiguous range found by binary
+//      search); the result is exact once the k-th distance is below the distance to the block
+//      boundary, otherwise the level is coarsened. The start level comes from the common prefix of
+//      the query's Morton neighbours, so dense (near) and sparse (far) regions both scan O(100) points.
+//   3. neighbours ordered by (float distance, index) exactly like the oracle; covariance in fp64;
+//      symmetric 3x3 eigen-decomposition by cyclic Jacobi (fp64) gives the SVD of the PSD matrix.
+// Float distances are accumulated x,y,z without FMA contraction so the neighbour sets match the
+// CPU oracle bit for bit.
+
+#include "covariance.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <float.h>
+#include <limits.h>
+
+namespace rolo {
+
+namespace {
+
+constexpr int MORTON_BITS = 21;
+
+__device__ __forceinline__ int float_to_ordered(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
+__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+__global__ void bbox_init_kernel(int* bbox) {
+  if (threadIdx.x < 3) bbox[threadIdx.x] = INT_MAX;
+  else if (threadIdx.x < 6) bbox[threadIdx.x] = INT_MIN;
+}
+
+__global__ void bbox_kernel(const float4* __restrict__ pts, int n, int* bbox) {
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+  }
+  #pragma unroll
+  for (int d = 0; d < 3; d++) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    #pragma unroll
+    for (int d = 0; d < 3; d++) {
+      atomicMin(&bbox[d], float_to_ordered(mn[d]));
+      atomicMax(&bbox[3 + d], float_to_ordered(mx[d]));
+    }
+  }
+}
+
+struct Quant {           // derived from the bbox on the fly by every kernel (no host round trip)
+  double mn[3];
+  double scale;          // finest cells per metre
+  double cell;           // finest cell size (metres)
+};
+
+__device__ __forceinline__ Quant make_quant(const int* bbox) {
+  Quant q;
+  double ext = 0.0;
+  #pragma unroll
+  for (int d = 0; d < 3; d++) {
+    q.mn[d] = (double)ordered_to_float(bbox[d]);
+    ext = fmax(ext, (double)ordered_to_float(bbox[3 + d]) - q.mn[d]);
+  }
+  ext = fmax(ext, 1e-6) * (1.0 + 1e-6);
+  q.cell = ext / (double)(1 << MORTON_BITS);
+  q.scale = 1.0 / q.cell;
+  return q;
+}
+
+__device__ __forceinline__ unsigned long long expand21(unsigned v) {   // spread 21 bits to every third bit
+  unsigned long long x = v & 0x1FFFFFull;
+  x = (x | x << 32) & 0x1F00000000FFFFull;
+  x = (x | x << 16) & 0x1F0000FF0000FFull;
+  x = (x | x << 8) & 0x100F00F00F00F00Full;
+  x = (x | x << 4) & 0x10C30C30C30C30C3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+__device__ __forceinline__ unsigned long long morton3(unsigned x, unsigned y, unsigned z) {
+  return expand21(x) | (expand21(y) << 1) | (expand21(z) << 2);
+}
+__device__ __forceinline__ void quantize(const Quant& q, float x, float y, float z, unsigned& ix, unsigned& iy, unsigned& iz) {
+  const double m = (double)((1 << MORTON_BITS) - 1);
+  ix = (unsigned)fmin(fmax(floor(((double)x - q.mn[0]) * q.scale), 0.0), m);
+  iy = (unsigned)fmin(fmax(floor(((double)y - q.mn[1]) * q.scale), 0.0), m);
+  iz = (unsigned)fmin(fmax(floor(((double)z - q.mn[2]) * q.scale), 0.0), m);
+}
+
+__global__ void morton_kernel(const float4* __restrict__ pts, int n, const int* __restrict__ bbox,
+                              unsigned long long* __restrict__ codes, int* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Quant q = make_quant(bbox);
+  const float4 p = pts[i];
+  unsigned ix, iy, iz;
+  quantize(q, p.x, p.y, p.z, ix, iy, iz);
+  codes[i] = morton3(ix, iy, iz);
+  idx[i] = i;
+}
+
+__global__ void gather_sorted_kernel(const float4* __restrict__ pts, const int* __restrict__ idx, int n, float4* __restrict__ sorted) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int i = idx[j];
+  float4 p = pts[i];
+  p.w = __int_as_float(i);
+  sorted[j] = p;
+}
+
+__device__ __forceinline__ int lower_bound_u64(const unsigned long long* __restrict__ a, int n, unsigned long long key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
+
+// top-k kept sorted ascending by (distance, index). K > 0: registers, fully unrolled.
+template <int K>
+struct TopKStatic {
+  float d[K]; int id[K];
+  __device__ __forceinline__ void reset(int) {
+    #pragma unroll
+    for (int t = 0; t < K; t++) { d[t] = FLT_MAX; id[t] = INT_MAX; }
+  }
+  __device__ __forceinline__ bool accepts(float dd, int ii, int) const { return cand_less(dd, ii, d[K - 1], id[K - 1]); }
+  __device__ __forceinline__ void insert(float dd, int ii, int) {
+    d[K - 1] = dd; id[K - 1] = ii;
+    #pragma unroll
+    for (int t = K - 1; t > 0; t--) {
+      const bool sw = cand_less(d[t], id[t], d[t - 1], id[t - 1]);
+      const float td = sw ? d[t - 1] : d[t]; const int ti = sw ? id[t - 1] : id[t];
+      d[t - 1] = sw ? d[t] : d[t - 1]; id[t - 1] = sw ? id[t] : id[t - 1];
+      d[t] = td; id[t] = ti;
+    }
+  }
+  __device__ __forceinline__ float worst(int) const { return d[K - 1]; }
+  __device__ __forceinline__ bool full(int) const { return id[K - 1] != INT_MAX; }
+  __device__ __forceinline__ int get(int t) const {
+    int r = 0;
+    #pragma unroll
+    for (int s = 0; s < K; s++) if (s == t) r = id[s];
+    return r;
+  }
+};
+
+// generic k (<= KCAP): local-memory arrays, insertion with early exit.
+constexpr int KCAP = 64;
+struct TopKDynamic {
+  float d[KCAP]; int id[KCAP];
+  __device__ __forceinline__ void reset(int k) { for (int t = 0; t < k; t++) { d[t] = FLT_MAX; id[t] = INT_MAX; } }
+  __device__ __forceinline__ bool accepts(float dd, int ii, int k) const { return cand_less(dd, ii, d[k - 1], id[k - 1]); }
+  __device__ __forceinline__ void insert(float dd, int ii, int k) {
+    int t = k - 1;
+    while (t > 0 && cand_less(dd, ii, d[t - 1], id[t - 1])) { d[t] = d[t - 1]; id[t] = id[t - 1]; t--; }
+    d[t] = dd; id[t] = ii;
+  }
+  __device__ __forceinline__ float worst(int k) const { return d[k - 1]; }
+  __device__ __forceinline__ bool full(int k) const { return id[k - 1] != INT_MAX; }
+  __device__ __forceinline__ int get(int t) const { return id[t]; }
+};
+
+// cyclic Jacobi eigen-decomposition of a symmetric 3x3 matrix (fp64). Q columns = eigenvectors.
+__device__ __forceinline__ void jacobi_rot(double& app, double& aqq, double& apq, double& arp, double& arq,
+                                           double& q0p, double& q0q, double& q1p, double& q1q, double& q2p, double& q2q) {
+  if (apq == 0.0) return;
+  const double theta = (aqq - app) / (2.0 * apq);
+  const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(theta * theta + 1.0));
+  const double c = rsqrt(t * t + 1.0);
+  const double s = t * c;
+  app -= t * apq; aqq += t * apq; apq = 0.0;
+  const double rp = c * arp - s * arq, rq = s * arp + c * arq; arp = rp; arq = rq;
+  double a, b;
+  a = c * q0p - s * q0q; b = s * q0p + c * q0q; q0p = a; q0q = b;
+  a = c * q1p - s * q1q; b = s * q1p + c * q1q; q1p = a; q1q = b;
+  a = c * q2p - s * q2q; b = s * q2p + c * q2q; q2p = a; q2q = b;
+}
+
+__device__ void eig3_sym(const double c[6], double lam[3], double Q[9]) {
+  double a00 = c[0], a01 = c[1], a02 = c[2], a11 = c[3], a12 = c[4], a22 = c[5];
+  double q00 = 1, q01 = 0, q02 = 0, q10 = 0, q11 = 1, q12 = 0, q20 = 0, q21 = 0, q22 = 1;
+  #pragma unroll 1
+  for (int sweep = 0; sweep < 12; sweep++) {
+    const double off = a01 * a01 + a02 * a02 + a12 * a12;
+    const double dg = a00 * a00 + a11 * a11 + a22 * a22;
+    if (off <= 1e-36 * dg || off == 0.0) break;
+    jacobi_rot(a00, a11, a01, a02, a12, q00, q01, q10, q11, q20, q21);   // (p,q) = (0,1), r = 2
+    jacobi_rot(a00, a22, a02, a01, a12, q00, q02, q10, q12, q20, q22);   // (0,2), r = 1
+    jacobi_rot(a11, a22, a12, a01, a02, q01, q02, q11, q12, q21, q22);   // (1,2), r = 0
+  }
+  lam[0] = a00; lam[1] = a11; lam[2] = a22;
+  Q[0] = q00; Q[1] = q01; Q[2] = q02; Q[3] = q10; Q[4] = q11; Q[5] = q12; Q[6] = q20; Q[7] = q21; Q[8] = q22;
+}
+
+__device__ __forceinline__ void inv3_sym(const double c[6], double o[6]) {
+  const double k0 = c[3] * c[5] - c[4] * c[4], k1 = c[2] * c[4] - c[1] * c[5], k2 = c[1] * c[4] - c[2] * c[3];
+  const double idet = 1.0 / (c[0] * k0 + c[1] * k1 + c[2] * k2);
+  o[0] = k0 * idet; o[1] = k1 * idet; o[2] = k2 * idet;
+  o[3] = (c[0] * c[5] - c[2] * c[2]) * idet; o[4] = (c[1] * c[2] - c[0] * c[4]) * idet; o[5] = (c[0] * c[3] - c[1] * c[1]) * idet;
+}
+
+// rot_vgicp_impl.hpp:458-492
+__device__ void regularize(const double cov[6], int method, double out[6]) {
+  if (method == 0 /*NONE*/) {
+    #pragma unroll
+    for (int t = 0; t < 6; t++) out[t] = cov[t];
+    return;
+  }
+  if (method == 4 /*FROBENIUS*/) {
+    double C[6] = {cov[0] + 1e-3, cov[1], cov[2], cov[3] + 1e-3, cov[4], cov[5] + 1e-3}, Ci[6];
+    inv3_sym(C, Ci);
+    const double fro = sqrt(Ci[0] * Ci[0] + Ci[3] * Ci[3] + Ci[5] * Ci[5] + 2.0 * (Ci[1] * Ci[1] + Ci[2] * Ci[2] + Ci[4] * Ci[4]));
+    #pragma unroll
+    for (int t = 0; t < 6; t++) Ci[t] /= fro;
+    inv3_sym(Ci, out);
+    return;
+  }
+  double lam[3], Q[9];
+  eig3_sym(cov, lam, Q);
+  // singular values |lam| sorted descending; U = Q sign(lam), V = Q
+  int o0 = 0, o1 = 1, o2 = 2;
+  double s0 = fabs(lam[0]), s1 = fabs(lam[1]), s2 = fabs(lam[2]);
+  if (s1 > s0) { double t = s0; s0 = s1; s1 = t; int u = o0; o0 = o1; o1 = u; }
+  if (s2 > s0) { double t = s0; s0 = s2; s2 = t; int u = o0; o0 = o2; o2 = u; }
+  if (s2 > s1) { double t = s1; s1 = s2; s2 = t; int u = o1; o1 = o2; o2 = u; }
+  double v0, v1, v2;
+  switch (method) {
+    case 3: /*PLANE*/ v0 = 1.0; v1 = 1.0; v2 = 1e-3; break;
+    case 1: /*MIN_EIG*/ v0 = fmax(s0, 1e-3); v1 = fmax(s1, 1e-3); v2 = fmax(s2, 1e-3); break;
+    case 2: /*NORMALIZED_MIN_EIG*/ v0 = fmax(s0 / s0, 1e-3); v1 = fmax(s1 / s0, 1e-3); v2 = fmax(s2 / s0, 1e-3); break;
+    default: /*PLANE_S*/ { const double sum = s0 + s1 + s2; v0 = s0 / sum; v1 = s1 / sum; v2 = 1e-3; } break;
+  }
+  const int ord[3] = {o0, o1, o2};
+  const double val[3] = {v0, v1, v2};
+  #pragma unroll
+  for (int t = 0; t < 6; t++) out[t] = 0.0;
+  #pragma unroll
+  for (int e = 0; e < 3; e++) {
+    const int col = ord[e];
+    double qx = 0, qy = 0, qz = 0, l = 0;
+    #pragma unroll
+    for (int cidx = 0; cidx < 3; cidx++) if (cidx == col) { qx = Q[0 + cidx]; qy = Q[3 + cidx]; qz = Q[6 + cidx]; l = lam[cidx]; }
+    const double sv = (l < 0.0) ? -val[e] : val[e];
+    out[0] += sv * qx * qx; out[1] += sv * qx * qy; out[2] += sv * qx * qz;
+    out[3] += sv * qy * qy; out[4] += sv * qy * qz; out[5] += sv * qz * qz;
+  }
+}
+
+template <typename TOPK>
+__global__ void __launch_bounds__(128)
+knn_cov_kernel(const float4* __restrict__ pts, const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes,
+               int n, int k, int method, const int* __restrict__ bbox, float* __restrict__ cov6, int* __restrict__ knn_out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const Quant qn = make_quant(bbox);
+  const float4 q = sorted[j];
+  const int self = __float_as_int(q.w);
+  unsigned ix, iy, iz;
+  quantize(qn, q.x, q.y, q.z, ix, iy, iz);
+  const double rel[3] = {(double)q.x - qn.mn[0], (double)q.y - qn.mn[1], (double)q.z - qn.mn[2]};
+
+  // start level: all points between the Morton neighbours j-4 .. j+4 share this many leading octree levels
+  int L;
+  {
+    const unsigned long long a = codes[max(j - 4, 0)], b = codes[min(j + 4, n - 1)];
+    const unsigned long long x = a ^ b;
+    const int common_bits = x ? (__clzll((long long)x) - 1) : 63;     // codes use 63 bits
+    L = min(common_bits / 3, MORTON_BITS);
+  }
+
+  TOPK top;
+  #pragma unroll 1
+  for (;; L--) {
+    top.reset(k);
+    const int sh = MORTON_BITS - L;
+    const int cx = (int)(ix >> sh), cy = (int)(iy >> sh), cz = (int)(iz >> sh);
+    const int ncell = 1 << L;
+    #pragma unroll 1
+    for (int o = 0; o < 27; o++) {
+      const int oo = (o == 0) ? 13 : (o <= 13 ? o - 1 : o);   // centre cell first
+      const int nx = cx + oo % 3 - 1, ny = cy + (oo / 3) % 3 - 1, nz = cz + oo / 9 - 1;
+      if (nx < 0 || ny < 0 || nz < 0 || nx >= ncell || ny >= ncell || nz >= ncell) continue;
+      const unsigned long long pre = morton3((unsigned)nx, (unsigned)ny, (unsigned)nz);
+      const unsigned long long klo = pre << (3 * sh);
+      const int lo = lower_bound_u64(codes, n, klo);
+      const int hi = (L == 0) ? n : lower_bound_u64(codes, n, (pre + 1ull) << (3 * sh));
+      for (int c = lo; c < hi; c++) {
+        const float4 p = __ldg(sorted + c);
+        const float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
+        float d = __fmul_rn(dx, dx);
+        d = __fadd_rn(d, __fmul_rn(dy, dy));
+        d = __fadd_rn(d, __fmul_rn(dz, dz));
+        const int pid = __float_as_int(p.w);
+        if (top.accepts(d, pid, k)) top.insert(d, pid, k);
+      }
+    }
+    if (L == 0) break;
+    // exact iff the k-th neighbour lies inside the guaranteed-complete radius of the scanned block
+    const double sL = qn.cell * (double)(1 << sh);
+    double rs = 1e300;
+    const int cc[3] = {cx, cy, cz};
+    #pragma unroll
+    for (int d = 0; d < 3; d++) {
+      if (cc[d] - 1 >= 0) rs = fmin(rs, rel[d] - (double)(cc[d] - 1) * sL);
+      if (cc[d] + 1 < ncell) rs = fmin(rs, (double)(cc[d] + 2) * sL - rel[d]);
+    }
+    if (top.full(k) && (double)top.worst(k) <= rs * rs * (1.0 - 1e-6)) break;
+  }
+
+  if (knn_out) for (int t = 0; t < k; t++) knn_out[(size_t)self * k + t] = top.get(t);
+  if (!cov6) return;
+
+  // mean-centred scatter / k, neighbours in (distance, index) order (rot_vgicp_impl.hpp:438-456)
+  double sx = 0, sy = 0, sz = 0;
+  for (int t = 0; t < k; t++) { const float4 p = __ldg(pts + top.get(t)); sx += (double)p.x; sy += (double)p.y; sz += (double)p.z; }
+  const double mx = sx / k, my = sy / k, mz = sz / k;
+  double c[6] = {0, 0, 0, 0, 0, 0};
+  for (int t = 0; t < k; t++) {
+    const float4 p = __ldg(pts + top.get(t));
+    const double dx = (double)p.x - mx, dy = (double)p.y - my, dz = (double)p.z - mz;
+    c[0] += dx * dx; c[1] += dx * dy; c[2] += dx * dz; c[3] += dy * dy; c[4] += dy * dz; c[5] += dz * dz;
+  }
+  #pragma unroll
+  for (int t = 0; t < 6; t++) c[t] /= (double)k;
+  double out[6];
+  regularize(c, method, out);
+  const size_t base = (size_t)(self / TILE_PTS) * COV_PLANES * TILE_PTS + (self % TILE_PTS);
+  #pragma unroll
+  for (int t = 0; t < 6; t++) cov6[base + (size_t)t * TILE_PTS] = (float)out[t];
+}
+
+}  // namespace
+
+size_t cov_cub_temp_bytes(int n) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
+                                  (const int*)nullptr, (int*)nullptr, n, 0, 3 * MORTON_BITS);
+  return bytes;
+}
+
+cudaError_t launch_covariances(const CovLaunch& L, cudaStream_t stream) {
+  if (L.n <= 0) return cudaSuccess;
+  if (L.k > KCAP || L.k < 1 || L.n < L.k) return cudaErrorInvalidValue;
+  const int n = L.n;
+  const int tb = 256, nb = (n + tb - 1) / tb;
+  bbox_init_kernel<<<1, 32, 0, stream>>>(L.s.bbox);
+  bbox_kernel<<<min(nb, 592), tb, 0, stream>>>(L.pts, n, L.s.bbox);
+  morton_kernel<<<nb, tb, 0, stream>>>(L.pts, n, L.s.bbox, L.s.codes_in, L.s.idx_in);
+  size_t temp = L.s.cub_temp_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(L.s.cub_temp, temp, L.s.codes_in, L.s.codes_out, L.s.idx_in, L.s.idx_out, n, 0,
+                                                  3 * MORTON_BITS, stream);
+  if (e != cudaSuccess) return e;
+  gather_sorted_kernel<<<nb, tb, 0, stream>>>(L.pts, L.s.idx_out, n, L.s.sorted);
+  const int kb = (n + 127) / 128;
+  if (L.k == 20) knn_cov_kernel<TopKStatic<20>><<<kb, 128, 0, stream>>>(L.pts, L.s.sorted, L.s.codes_out, n, L.k, L.method, L.s.bbox, L.cov6, L.knn_out);
+  else if (L.k == 10) knn_cov_kernel<TopKStatic<10>><<<kb, 128, 0, stream>>>(L.pts, L.s.sorted, L.s.codes_out, n, L.k, L.method, L.s.bbox, L.cov6, L.knn_out);
+  else knn_cov_kernel<TopKDynamic><<<kb, 128, 0, stream>>>(L.pts, L.s.sorted, L.s.codes_out, n, L.k, L.method, L.s.bbox, L.cov6, L.knn_out);
+  return cudaGetLastError();
+}
+
+}  // namespace rolo

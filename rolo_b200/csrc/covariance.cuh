@@ -1,0 +1,32 @@
+// covariance.cuh — launch interface of the exact-kNN covariance estimation.
+#pragma once
+#include "common.cuh"
+
+namespace rolo {
+
+struct CovScratch {           // all device pointers; sized for n points (see cov_scratch_bytes)
+  unsigned long long* codes_in;   // [n]
+  unsigned long long* codes_out;  // [n]
+  int* idx_in;                    // [n]
+  int* idx_out;                   // [n]
+  float4* sorted;                 // [n] xyz + original index (int bits in w)
+  void* cub_temp;
+  size_t cub_temp_bytes;
+  int* bbox;                      // [6] ordered-int min xyz / max xyz
+};
+
+size_t cov_cub_temp_bytes(int n);
+
+struct CovLaunch {
+  const float4* pts;          // [n] (w ignored)
+  int n;
+  int k;                      // neighbours incl. self (k_correspondences_)
+  int method;                 // RG_REG_*
+  float* cov6;                // out, tile-planar (may be null when only knn_out is wanted)
+  int* knn_out;               // optional [n*k] original indices sorted by (distance, index); may be null
+  CovScratch s;
+};
+
+cudaError_t launch_covariances(const CovLaunch& L, cudaStream_t stream);
+
+}  // namespace rolo

@@ -1,0 +1,344 @@
+// linearize.cu — the fused per-Gauss-Newton-iteration kernel (sm_100a).
+//
+// One launch evaluates, for every source point of every scan pair in the batch:
+//   p' = R p + t                                   (rot_vgicp_impl.hpp:184-185, 254)
+//   voxel key of p' -> hash probe (+ neighbour offsets) (rot_vgicp_impl.hpp:186-193, vmp_voxel.hpp:199-233)
+//   M = (B_v + Rm A Rm^T)^-1                        (rot_vgicp_impl.hpp:204-221; 3x3 block of the 4x4 form)
+//   e = mu_v - p', w = sqrt(n_v), cost += w e^T M e (rot_vgicp_impl.hpp:256-259)
+//   H += w J^T M J, b += w J^T M e, J = [skew(p') | -I]   (rot_vgicp_impl.hpp:265-277 / 345-372 / 574-590)
+// and tree-reduces the 28 unique sums (+ correspondence count) to one 32-double result per pair:
+// warp shuffles -> shared memory -> per-CTA partial -> last-CTA fixed-order final pass (deterministic).
+//
+// Data movement: source points (float4) and covariances (tile-planar 6 x fp32) stream through shared
+// memory as 4 KB + 6 KB tiles with 1-D TMA bulk copies (cp.async.bulk + mbarrier, double-buffered);
+// the voxel table/payload gathers go through the read-only path (L1/L2 resident). All arithmetic
+// that decides a voxel or enters a sum is fp64 (fp32 is only a pre-filter for the key).
+// No tensor cores: there is no dense contraction in this path.
+
+#include "linearize.cuh"
+#include <string.h>
+
+namespace rolo {
+
+namespace {
+
+constexpr int NTHREADS = TILE_PTS;               // 256
+constexpr int NWARPS = NTHREADS / 32;
+constexpr uint32_t PTS_TILE_BYTES = TILE_PTS * sizeof(float4);             // 4096
+constexpr uint32_t COV_TILE_BYTES = TILE_PTS * COV_PLANES * sizeof(float); // 6144
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+  #pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int NOFF>
+__device__ __forceinline__ void neighbor_offset(int o, int& dx, int& dy, int& dz) {
+  if (NOFF == 1) { dx = dy = dz = 0; }
+  else if (NOFF == 7) {   // vmp_voxel.hpp:23-31 order
+    dx = (o == 1) - (o == 2); dy = (o == 3) - (o == 4); dz = (o == 5) - (o == 6);
+  } else {                // vmp_voxel.hpp:38-46 order
+    dx = o / 9 - 1; dy = (o / 3) % 3 - 1; dz = o % 3 - 1;
+  }
+}
+
+// number of accumulators actually used per mode
+template <int MODE> struct AccN { static constexpr int value = (MODE == LIN_SE3) ? 29 : (MODE == LIN_SO3 ? 11 : 2); };
+// SE3 : [0..5] Mw, [6..14] G, [15..20] StG, [21..23] q, [24..26] Stq, [27] cost, [28] count
+// SO3 : [0..5] StG, [6..8] Stq, [9] cost, [10] count
+// COST: [0] cost, [1] count
+
+template <int MODE, bool REFRESH, int NOFF>
+__global__ void __launch_bounds__(NTHREADS, 2)
+linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict__ dyn_arr, const __grid_constant__ LinDyn dyn0, int blocks_per_pair) {
+  constexpr int NACC = AccN<MODE>::value;
+  __shared__ __align__(128) float4 s_pts[2][TILE_PTS];
+  __shared__ __align__(128) float s_cov[2][COV_PLANES * TILE_PTS];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ LinDyn s_dyn;
+  __shared__ double s_red[NWARPS][RES_USED];
+  __shared__ int s_is_last;
+
+  const int tid = threadIdx.x;
+  const int pair = blockIdx.y;
+  const int blk = blockIdx.x;
+  const LinStatic& st = st_arr[pair];
+
+  // stage the per-evaluation pose block into shared memory (uniform operands for every thread)
+  {
+    const double* src = dyn_arr ? reinterpret_cast<const double*>(dyn_arr + pair) : reinterpret_cast<const double*>(&dyn0);
+    double* dst = reinterpret_cast<double*>(&s_dyn);
+    for (int k = tid; k < (int)(sizeof(LinDyn) / sizeof(double)); k += NTHREADS) dst[k] = src[k];
+  }
+  if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
+  __syncthreads();
+
+  const int n = st.n;
+  const int ntiles = (n + TILE_PTS - 1) / TILE_PTS;
+  const float4* __restrict__ g_pts = st.src;
+  const float* __restrict__ g_cov = st.cov6;
+  const VoxSlot* __restrict__ table = st.table;
+  const VoxPayload* __restrict__ vox = st.vox;
+  int* __restrict__ corr = st.corr;
+  const unsigned mask = st.mask;
+
+  double acc[NACC];
+  #pragma unroll
+  for (int k = 0; k < NACC; k++) acc[k] = 0.0;
+
+  // prologue: first tile of this CTA
+  if (tid == 0 && blk < ntiles) {
+    mbar_arrive_expect_tx(&s_bar[0], PTS_TILE_BYTES + COV_TILE_BYTES);
+    tma_load_1d(&s_pts[0][0], g_pts + (size_t)blk * TILE_PTS, PTS_TILE_BYTES, &s_bar[0]);
+    tma_load_1d(&s_cov[0][0], g_cov + (size_t)blk * COV_PLANES * TILE_PTS, COV_TILE_BYTES, &s_bar[0]);
+  }
+
+  int it = 0;
+  for (int tile = blk; tile < ntiles; tile += blocks_per_pair, it++) {
+    const int stage = it & 1;
+    const int next = tile + blocks_per_pair;
+    if (tid == 0 && next < ntiles) {   // prefetch the next tile into the other buffer (freed by the trailing __syncthreads)
+      mbar_arrive_expect_tx(&s_bar[stage ^ 1], PTS_TILE_BYTES + COV_TILE_BYTES);
+      tma_load_1d(&s_pts[stage ^ 1][0], g_pts + (size_t)next * TILE_PTS, PTS_TILE_BYTES, &s_bar[stage ^ 1]);
+      tma_load_1d(&s_cov[stage ^ 1][0], g_cov + (size_t)next * COV_PLANES * TILE_PTS, COV_TILE_BYTES, &s_bar[stage ^ 1]);
+    }
+    mbar_wait(&s_bar[stage], (it >> 1) & 1);
+
+    const int i = tile * TILE_PTS + tid;
+    if (i < n) {
+      const float4 pf = s_pts[stage][tid];
+      const double px = (double)pf.x, py = (double)pf.y, pz = (double)pf.z;
+      // p' = R p + t
+      const double x = s_dyn.R[0] * px + s_dyn.R[1] * py + s_dyn.R[2] * pz + s_dyn.t[0];
+      const double y = s_dyn.R[3] * px + s_dyn.R[4] * py + s_dyn.R[5] * pz + s_dyn.t[1];
+      const double z = s_dyn.R[6] * px + s_dyn.R[7] * py + s_dyn.R[8] * pz + s_dyn.t[2];
+
+      int cx = 0, cy = 0, cz = 0;
+      if (REFRESH) voxel_coord(st.grid, x, y, z, cx, cy, cz);
+
+      // C_A = Rm A Rm^T (symmetric), computed lazily on the first hit
+      double ca0 = 0, ca1 = 0, ca2 = 0, ca3 = 0, ca4 = 0, ca5 = 0;
+      bool have_ca = false;
+
+      #pragma unroll 1
+      for (int o = 0; o < NOFF; o++) {
+        int id;
+        if (REFRESH) {
+          int dx, dy, dz;
+          neighbor_offset<NOFF>(o, dx, dy, dz);
+          id = table_lookup(table, mask, cx + dx, cy + dy, cz + dz);
+          corr[(size_t)i * NOFF + o] = id;
+        } else {
+          id = corr[(size_t)i * NOFF + o];
+        }
+        if (id < 0) continue;
+
+        if (!have_ca) {
+          have_ca = true;
+          const float* cv = &s_cov[stage][tid];
+          const double a0 = (double)cv[0 * TILE_PTS], a1 = (double)cv[1 * TILE_PTS], a2 = (double)cv[2 * TILE_PTS];
+          const double a3 = (double)cv[3 * TILE_PTS], a4 = (double)cv[4 * TILE_PTS], a5 = (double)cv[5 * TILE_PTS];
+          const double r0 = s_dyn.Rm[0], r1 = s_dyn.Rm[1], r2 = s_dyn.Rm[2];
+          const double r3 = s_dyn.Rm[3], r4 = s_dyn.Rm[4], r5 = s_dyn.Rm[5];
+          const double r6 = s_dyn.Rm[6], r7 = s_dyn.Rm[7], r8 = s_dyn.Rm[8];
+          const double t00 = r0 * a0 + r1 * a1 + r2 * a2, t01 = r0 * a1 + r1 * a3 + r2 * a4, t02 = r0 * a2 + r1 * a4 + r2 * a5;
+          const double t10 = r3 * a0 + r4 * a1 + r5 * a2, t11 = r3 * a1 + r4 * a3 + r5 * a4, t12 = r3 * a2 + r4 * a4 + r5 * a5;
+          const double t20 = r6 * a0 + r7 * a1 + r8 * a2, t21 = r6 * a1 + r7 * a3 + r8 * a4, t22 = r6 * a2 + r7 * a4 + r8 * a5;
+          ca0 = t00 * r0 + t01 * r1 + t02 * r2;
+          ca1 = t00 * r3 + t01 * r4 + t02 * r5;
+          ca2 = t00 * r6 + t01 * r7 + t02 * r8;
+          ca3 = t10 * r3 + t11 * r4 + t12 * r5;
+          ca4 = t10 * r6 + t11 * r7 + t12 * r8;
+          ca5 = t20 * r6 + t21 * r7 + t22 * r8;
+        }
+
+        // voxel payload gather: 80 B as 5 x 16 B read-only loads
+        const double2* vp = reinterpret_cast<const double2*>(vox + id);
+        const double2 v0 = __ldg(vp + 0), v1 = __ldg(vp + 1), v2 = __ldg(vp + 2), v3 = __ldg(vp + 3), v4 = __ldg(vp + 4);
+        const double mx = v0.x, my = v0.y, mz = v1.x;
+        const double c0 = v1.y + ca0, c1 = v2.x + ca1, c2 = v2.y + ca2, c3 = v3.x + ca3, c4 = v3.y + ca4, c5 = v4.x + ca5;
+        const double w = v4.y;
+
+        // M = C^-1 by cofactors (symmetric)
+        const double k0 = c3 * c5 - c4 * c4;
+        const double k1 = c2 * c4 - c1 * c5;
+        const double k2 = c1 * c4 - c2 * c3;
+        const double det = c0 * k0 + c1 * k1 + c2 * k2;
+        const double idet = 1.0 / det;
+        const double m0 = k0 * idet, m1 = k1 * idet, m2 = k2 * idet;
+        const double m3 = (c0 * c5 - c2 * c2) * idet;
+        const double m4 = (c1 * c2 - c0 * c4) * idet;
+        const double m5 = (c0 * c3 - c1 * c1) * idet;
+
+        // residuals
+        const double ex = mx - x, ey = my - y, ez = mz - z;
+        const double qx = m0 * ex + m1 * ey + m2 * ez;
+        const double qy = m1 * ex + m3 * ey + m4 * ez;
+        const double qz = m2 * ex + m4 * ey + m5 * ez;
+        double cost = ex * qx + ey * qy + ez * qz;
+        // continuous-time term (t3 modes; lam_c = 0 otherwise)  rot_vgicp_impl.hpp:548,555
+        const double lam_c = s_dyn.lam_c;
+        double bx = qx, by = qy, bz = qz;      // M e_b with e_b = e + b_ct_scale * ct
+        if (lam_c != 0.0) {
+          const double tx = s_dyn.ct[0], ty = s_dyn.ct[1], tz = s_dyn.ct[2];
+          const double ux = m0 * tx + m1 * ty + m2 * tz;
+          const double uy = m1 * tx + m3 * ty + m4 * tz;
+          const double uz = m2 * tx + m4 * ty + m5 * tz;
+          cost += lam_c * (tx * ux + ty * uy + tz * uz);
+          bx += s_dyn.b_ct_scale * ux; by += s_dyn.b_ct_scale * uy; bz += s_dyn.b_ct_scale * uz;
+        }
+
+        if (MODE == LIN_COST) {
+          acc[0] += w * cost;
+          acc[1] += 1.0;
+        } else {
+          const double ws = w * s_dyn.h_scale;
+          // G = M S, S = skew(p') = [[0,-z,y],[z,0,-x],[-y,x,0]]
+          const double g00 = m1 * z - m2 * y, g01 = m2 * x - m0 * z, g02 = m0 * y - m1 * x;
+          const double g10 = m3 * z - m4 * y, g11 = m4 * x - m1 * z, g12 = m1 * y - m3 * x;
+          const double g20 = m4 * z - m5 * y, g21 = m5 * x - m2 * z, g22 = m2 * y - m4 * x;
+          // S^T G (symmetric), S^T = [[0,z,-y],[-z,0,x],[y,-x,0]]
+          const double h00 = z * g10 - y * g20, h01 = z * g11 - y * g21, h02 = z * g12 - y * g22;
+          const double h11 = x * g21 - z * g01, h12 = x * g22 - z * g02;
+          const double h22 = y * g02 - x * g12;
+          // S^T (M e_b)
+          const double sx = z * by - y * bz, sy = x * bz - z * bx, sz = y * bx - x * by;
+          if (MODE == LIN_SE3) {
+            acc[0] += ws * m0; acc[1] += ws * m1; acc[2] += ws * m2; acc[3] += ws * m3; acc[4] += ws * m4; acc[5] += ws * m5;
+            acc[6] += ws * g00; acc[7] += ws * g01; acc[8] += ws * g02;
+            acc[9] += ws * g10; acc[10] += ws * g11; acc[11] += ws * g12;
+            acc[12] += ws * g20; acc[13] += ws * g21; acc[14] += ws * g22;
+            acc[15] += ws * h00; acc[16] += ws * h01; acc[17] += ws * h02; acc[18] += ws * h11; acc[19] += ws * h12; acc[20] += ws * h22;
+            acc[21] += w * bx; acc[22] += w * by; acc[23] += w * bz;
+            acc[24] += w * sx; acc[25] += w * sy; acc[26] += w * sz;
+            acc[27] += w * cost;
+            acc[28] += 1.0;
+          } else {
+            acc[0] += ws * h00; acc[1] += ws * h01; acc[2] += ws * h02; acc[3] += ws * h11; acc[4] += ws * h12; acc[5] += ws * h22;
+            acc[6] += w * sx; acc[7] += w * sy; acc[8] += w * sz;
+            acc[9] += w * cost;
+            acc[10] += 1.0;
+          }
+        }
+      }
+    }
+    __syncthreads();   // every thread is done with buffer `stage` before it is refilled
+  }
+
+  // ---- reduction: warp shuffle tree -> shared -> CTA partial -> last-CTA final pass ---------------
+  const int lane = tid & 31, warp = tid >> 5;
+  #pragma unroll
+  for (int k = 0; k < NACC; k++) {
+    const double v = warp_sum(acc[k]);
+    if (lane == 0) s_red[warp][k] = v;
+  }
+  __syncthreads();
+  double* partial = st.partials + (size_t)blk * RES_N;
+  if (tid < NACC) {
+    double v = 0.0;
+    #pragma unroll
+    for (int wq = 0; wq < NWARPS; wq++) v += s_red[wq][tid];
+    partial[tid] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned ticket = atomicAdd(st.counter, 1u);
+    s_is_last = (ticket == (unsigned)blocks_per_pair - 1u);
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+
+  // last CTA of this pair: fixed-order sum over the CTA partials (deterministic for a given launch shape)
+  {
+    const int c = tid & 31, g = tid >> 5;
+    double v = 0.0;
+    if (c < NACC) {
+      const volatile double* pp = st.partials;
+      for (int b = g; b < blocks_per_pair; b += NWARPS) v += pp[(size_t)b * RES_N + c];
+      s_red[g][c] = v;
+    }
+    __syncthreads();
+    if (tid < RES_N) {
+      double tot = 0.0;
+      if (tid < NACC) {
+        #pragma unroll
+        for (int gq = 0; gq < NWARPS; gq++) tot += s_red[gq][tid];
+      }
+      // scatter the mode-specific accumulator layout into the common 32-double result layout
+      int dst = -1;
+      if (MODE == LIN_SE3) dst = tid < NACC ? tid : -1;
+      else if (MODE == LIN_SO3) dst = tid < 6 ? 15 + tid : (tid < 9 ? 24 + (tid - 6) : (tid == 9 ? 27 : (tid == 10 ? 28 : -1)));
+      else dst = tid == 0 ? 27 : (tid == 1 ? 28 : -1);
+      if (dst >= 0) st.result[dst] = tot;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      *st.counter = 0u;                       // re-arm for the next launch
+      if (st.done_flag) {
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned*>(st.done_flag) = s_dyn.seq;
+      }
+    }
+  }
+}
+
+template <int MODE, bool REFRESH, int NOFF>
+cudaError_t launch_t(const LinLaunch& L, const LinDyn& dyn0, cudaStream_t stream) {
+  dim3 grid((unsigned)L.blocks_per_pair, (unsigned)L.n_pairs, 1);
+  linearize_kernel<MODE, REFRESH, NOFF><<<grid, NTHREADS, 0, stream>>>(L.st, L.dyn, dyn0, L.blocks_per_pair);
+  return cudaGetLastError();
+}
+
+template <int NOFF>
+cudaError_t launch_n(const LinLaunch& L, const LinDyn& dyn0, cudaStream_t stream) {
+  if (L.mode == LIN_SE3) return L.refresh ? launch_t<LIN_SE3, true, NOFF>(L, dyn0, stream) : launch_t<LIN_SE3, false, NOFF>(L, dyn0, stream);
+  if (L.mode == LIN_SO3) return L.refresh ? launch_t<LIN_SO3, true, NOFF>(L, dyn0, stream) : launch_t<LIN_SO3, false, NOFF>(L, dyn0, stream);
+  return L.refresh ? launch_t<LIN_COST, true, NOFF>(L, dyn0, stream) : launch_t<LIN_COST, false, NOFF>(L, dyn0, stream);
+}
+
+}  // namespace
+
+cudaError_t launch_linearize(const LinLaunch& L, const LinDyn* dyn0, cudaStream_t stream) {
+  LinDyn zero;
+  if (!dyn0) { memset(&zero, 0, sizeof(zero)); dyn0 = &zero; }
+  if (!L.dyn && dyn0 == &zero) return cudaErrorInvalidValue;
+  switch (L.noff) {
+    case 1: return launch_n<1>(L, *dyn0, stream);
+    case 7: return launch_n<7>(L, *dyn0, stream);
+    case 27: return launch_n<27>(L, *dyn0, stream);
+  }
+  return cudaErrorInvalidValue;
+}
+
+int linearize_max_blocks_per_sm() {
+  int nb = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, linearize_kernel<LIN_SE3, true, 1>, NTHREADS, 0);
+  return nb;
+}
+
+}  // namespace rolo

@@ -109,7 +109,8 @@ def raycast(scene: dict, T_ws: np.ndarray, dirs_s: np.ndarray) -> np.ndarray:
 def ray_dirs(sensor: str) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
     rings, cols, e0, e1 = SENSORS[sensor]
     elev = np.deg2rad(np.linspace(e0, e1, rings))
-    az = -np.pi + 2.0 * np.pi * (np.arange(cols) + 0.5) / cols
+    # azimuth of column c sits at the centre of imageProjection's column c (imageProjection.cpp:438-444)
+    az = -np.pi + 2.0 * np.pi * np.arange(cols) / cols
     ee, aa = np.meshgrid(elev, az, indexing="ij")
     d = np.stack([np.cos(ee) * np.cos(aa), np.cos(ee) * np.sin(aa), np.sin(ee)], axis=-1).reshape(-1, 3)
     ring = np.repeat(np.arange(rings), cols)
