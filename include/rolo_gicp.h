@@ -158,6 +158,11 @@ rg_ctx* rg_batch_ctx(rg_batch*, int pair);      /* per-pair context for setters 
 int  rg_batch_align(rg_batch*, const float* guesses /* n_pairs*16 or NULL */, float* final_transformations /* n_pairs*16 */);
 double rg_batch_last_linearize_us(const rg_batch*);   /* mean device time of the fused launches (CUDA events) */
 int    rg_batch_last_linearize_launches(const rg_batch*);
+void*  rg_batch_stream(const rg_batch*);               /* cudaStream_t the batch launches on (for event timing) */
+void*  rg_stream(const rg_ctx*);                       /* cudaStream_t of a stand-alone context           */
+/* number of this library's own kernels launched so far in this process (library-internal kernels of
+ * cub's radix sort are not counted) */
+unsigned long long rg_kernel_launch_count(void);
 
 /* ---- sharded single registration (BASELINE config 4): reduction hook ----------------------------------
  * When set, every linearize/compute_error result (32 doubles: 28 packed sums + count + pad) is passed

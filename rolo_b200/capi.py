@@ -74,6 +74,9 @@ def load():
     L.rg_batch_last_linearize_us.restype = C.c_double
     L.rg_batch_ctx.restype = C.c_void_p
     L.rg_batch_destroy.restype = None
+    L.rg_batch_stream.restype = C.c_void_p
+    L.rg_stream.restype = C.c_void_p
+    L.rg_kernel_launch_count.restype = C.c_ulonglong
     sz, vp, d, f, i = C.c_size_t, C.c_void_p, C.c_double, C.c_float, C.c_int
     protos = {
         "rg_set_resolution": [vp, d], "rg_set_polar_resolution": [vp, d, d, d], "rg_set_voxel_accumulation_mode": [vp, i],
@@ -97,7 +100,7 @@ def load():
         "rg_knn": [vp, i, i, ip], "rg_last_kernel_us": [vp],
         "rg_batch_create": [i, i, C.POINTER(vp)], "rg_batch_destroy": [vp], "rg_batch_ctx": [vp, i],
         "rg_batch_align": [vp, fp, fp], "rg_batch_last_linearize_us": [vp], "rg_batch_last_linearize_launches": [vp],
-        "rg_set_reduce_hook": [vp, REDUCE_FN, vp, i],
+        "rg_set_reduce_hook": [vp, REDUCE_FN, vp, i], "rg_batch_stream": [vp], "rg_stream": [vp], "rg_kernel_launch_count": [],
     }
     for name, args in protos.items():
         getattr(L, name).argtypes = args

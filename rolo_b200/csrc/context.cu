@@ -28,6 +28,7 @@ namespace {
 
 std::mutex g_mutex;
 std::string g_last_error;
+std::atomic<unsigned long long> g_launches{0};   // own kernels launched (bench.py's gpu_launches claim)
 std::atomic<unsigned> g_seq{0};   // launch sequence numbers written to the mapped completion flags
 
 // ------------------------------------------------------------------------------------------------
@@ -226,6 +227,7 @@ struct rg_ctx {
   DevBuf<int> idx_in, idx_out, bbox;
   DevBuf<float4> sorted;
   DevBuf<unsigned char> cub_temp;
+  DevBuf<int> knn_idx;
 
   // linearize
   DevBuf<int> corr; int corr_noff = 0;
@@ -313,6 +315,7 @@ int upload_cloud(rg_ctx* c, Cloud& cl, const float* host, size_t n, size_t strid
   if (n == 0) return RG_OK;
   RG_CUDA(c, c->staging.ensure(c->device, n * stride_bytes));
   RG_CUDA(c, cudaMemcpyAsync(c->staging.p, host, n * stride_bytes, cudaMemcpyHostToDevice, c->stream));
+  g_launches++;
   extract_points_kernel<<<(n_pad + 255) / 256, 256, 0, c->stream>>>(c->staging.p, stride_bytes, (int)n, n_pad, cl.pts.p);
   RG_CUDA(c, cudaGetLastError());
   RG_CUDA(c, cudaStreamSynchronize(c->stream));   // contract: the host buffer is consumed before returning
@@ -334,6 +337,7 @@ int upload_cloud_device(rg_ctx* c, Cloud& cl, const float* dev, size_t n, cudaSt
     cudaStreamWaitEvent(c->stream, ev, 0);
     cudaEventDestroy(ev);
   }
+  g_launches++;
   copy_points_kernel<<<(n_pad + 255) / 256, 256, 0, c->stream>>>(reinterpret_cast<const float4*>(dev), (int)n, n_pad, cl.pts.p);
   RG_CUDA(c, cudaGetLastError());
   return RG_OK;
@@ -353,14 +357,16 @@ int calc_cov(rg_ctx* c, Cloud& cl) {
   RG_CUDA(c, c->sorted.ensure(c->device, n)); RG_CUDA(c, c->bbox.ensure(c->device, 8));
   const size_t tb = cov_cub_temp_bytes(n);
   RG_CUDA(c, c->cub_temp.ensure(c->device, tb));
+  RG_CUDA(c, c->knn_idx.ensure(c->device, (size_t)n * c->k_correspondences));
   CovLaunch L;
   L.pts = cl.pts.p; L.n = n; L.k = c->k_correspondences; L.method = c->regularization_method;
-  L.cov6 = cl.cov6.p; L.knn_out = nullptr;
+  L.cov6 = cl.cov6.p; L.knn = c->knn_idx.p;
   L.s.codes_in = c->codes_in.p; L.s.codes_out = c->codes_out.p; L.s.idx_in = c->idx_in.p; L.s.idx_out = c->idx_out.p;
   L.s.sorted = c->sorted.p; L.s.cub_temp = c->cub_temp.p; L.s.cub_temp_bytes = tb; L.s.bbox = c->bbox.p;
   // zero the padding rows of the covariance tiles (only the last tile has any)
   if (cl.n_pad > n) RG_CUDA(c, cudaMemsetAsync(cl.cov6.p + (size_t)(cl.n_pad / TILE_PTS - 1) * COV_PLANES * TILE_PTS, 0, sizeof(float) * COV_PLANES * TILE_PTS, c->stream));
   RG_CUDA(c, launch_covariances(L, c->stream));
+  g_launches += 6;   // bbox_init, bbox, morton, gather, knn, cov (cub's radix-sort kernels not counted)
   cl.has_cov = true;
   return RG_OK;
 }
@@ -397,6 +403,7 @@ int build_voxelmap(rg_ctx* c) {
   b.table = c->table.p; b.mask = c->mask; b.slot_of_point = c->slot_of_point.p; b.counters = c->counters.p;
   b.sums = c->sums.p; b.vox = c->vox.p;
   RG_CUDA(c, launch_voxel_build(b, c->stream));
+  g_launches += 3;
   c->voxel_ok = true; c->n_vox = -1; c->st_ok = false; c->have_corr = false;
   return RG_OK;
 }
@@ -552,6 +559,7 @@ int evaluate_single(rg_ctx* c, const host::Request& r, const double* g3, const d
   L.st = c->st_dev.p; L.dyn = nullptr;
   if (c->profile) cudaEventRecord(c->ev0, c->stream);
   RG_CUDA(c, launch_linearize(L, &d, c->stream));
+  g_launches++;
   if (c->profile) cudaEventRecord(c->ev1, c->stream);
   const bool on_dev = c->reduce_fn && c->reduce_on_device && !c->batch;
   if (on_dev) {
@@ -639,7 +647,7 @@ void rg_destroy(rg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->src.release(); c->tgt.release();
   c->table.release(); c->vox.release(); c->sums.release(); c->slot_of_point.release(); c->counters.release();
-  c->codes_in.release(); c->codes_out.release(); c->idx_in.release(); c->idx_out.release(); c->bbox.release(); c->sorted.release(); c->cub_temp.release();
+  c->codes_in.release(); c->codes_out.release(); c->idx_in.release(); c->idx_out.release(); c->bbox.release(); c->sorted.release(); c->cub_temp.release(); c->knn_idx.release();
   c->corr.release(); c->partials.release(); c->counter.release(); c->result_dev.release(); c->st_dev.release(); c->staging.release();
   if (c->result_host) pool().pinned_free(c->result_host);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -915,7 +923,7 @@ int rg_knn(rg_ctx* c, int which, int k, int32_t* out) {
   DevBuf<int> dk;
   RG_CUDA(c, dk.ensure(c->device, (size_t)n * k));
   CovLaunch L;
-  L.pts = cl.pts.p; L.n = n; L.k = k; L.method = c->regularization_method; L.cov6 = nullptr; L.knn_out = dk.p;
+  L.pts = cl.pts.p; L.n = n; L.k = k; L.method = c->regularization_method; L.cov6 = nullptr; L.knn = dk.p;
   L.s.codes_in = c->codes_in.p; L.s.codes_out = c->codes_out.p; L.s.idx_in = c->idx_in.p; L.s.idx_out = c->idx_out.p;
   L.s.sorted = c->sorted.p; L.s.cub_temp = c->cub_temp.p; L.s.cub_temp_bytes = tb; L.s.bbox = c->bbox.p;
   RG_CUDA(c, launch_covariances(L, c->stream));
@@ -980,6 +988,9 @@ void rg_batch_destroy(rg_batch* b) {
 rg_ctx* rg_batch_ctx(rg_batch* b, int pair) { return (b && pair >= 0 && pair < (int)b->pairs.size()) ? b->pairs[pair] : nullptr; }
 double rg_batch_last_linearize_us(const rg_batch* b) { return (b && b->lin_launches) ? b->lin_us_sum / b->lin_launches : -1.0; }
 int rg_batch_last_linearize_launches(const rg_batch* b) { return b ? b->lin_launches : 0; }
+void* rg_batch_stream(const rg_batch* b) { return b ? (void*)b->stream : nullptr; }
+void* rg_stream(const rg_ctx* c) { return c ? (void*)c->stream : nullptr; }
+unsigned long long rg_kernel_launch_count(void) { return g_launches.load(); }
 
 int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
   if (!b || !out_T) return set_err(nullptr, RG_ERR_INVALID, "rg_batch_align: bad arguments");
@@ -1042,6 +1053,7 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
       L.mode = mode; L.refresh = refresh; L.noff = noff; L.n_pairs = G; L.blocks_per_pair = bpp; L.st = st_arr; L.dyn = b->dyn_dev.p;
       cudaEventRecord(b->ev0, b->stream);
       RG_CUDA(nullptr, launch_linearize(L, nullptr, b->stream));
+      g_launches++;
       cudaEventRecord(b->ev1, b->stream);
       for (int gi = 0; gi < G; gi++) {
         rg_ctx* c = b->pairs[group[gi]];

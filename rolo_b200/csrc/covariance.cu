@@ -50,12 +50,19 @@ __global__ void bbox_kernel(const float4* __restrict__ pts, int n, int* bbox) {
       mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
     }
   }
-  if ((threadIdx.x & 31) == 0) {
+  __shared__ float s_mn[3][8], s_mx[3][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
     #pragma unroll
-    for (int d = 0; d < 3; d++) {
-      atomicMin(&bbox[d], float_to_ordered(mn[d]));
-      atomicMax(&bbox[3 + d], float_to_ordered(mx[d]));
-    }
+    for (int d = 0; d < 3; d++) { s_mn[d][warp] = mn[d]; s_mx[d][warp] = mx[d]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int d = threadIdx.x;
+    float a = s_mn[d][0], b = s_mx[d][0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) { a = fminf(a, s_mn[d][w]); b = fmaxf(b, s_mx[d][w]); }
+    atomicMin(&bbox[d], float_to_ordered(a));
+    atomicMax(&bbox[3 + d], float_to_ordered(b));
   }
 }
 
@@ -129,35 +136,6 @@ __device__ __forceinline__ int lower_bound_u64(const unsigned long long* __restr
 }
 
 __device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
-
-// top-k kept sorted ascending by (distance, index). K > 0: registers, fully unrolled.
-template <int K>
-struct TopKStatic {
-  float d[K]; int id[K];
-  __device__ __forceinline__ void reset(int) {
-    #pragma unroll
-    for (int t = 0; t < K; t++) { d[t] = FLT_MAX; id[t] = INT_MAX; }
-  }
-  __device__ __forceinline__ bool accepts(float dd, int ii, int) const { return cand_less(dd, ii, d[K - 1], id[K - 1]); }
-  __device__ __forceinline__ void insert(float dd, int ii, int) {
-    d[K - 1] = dd; id[K - 1] = ii;
-    #pragma unroll
-    for (int t = K - 1; t > 0; t--) {
-      const bool sw = cand_less(d[t], id[t], d[t - 1], id[t - 1]);
-      const float td = sw ? d[t - 1] : d[t]; const int ti = sw ? id[t - 1] : id[t];
-      d[t - 1] = sw ? d[t] : d[t - 1]; id[t - 1] = sw ? id[t] : id[t - 1];
-      d[t] = td; id[t] = ti;
-    }
-  }
-  __device__ __forceinline__ float worst(int) const { return d[K - 1]; }
-  __device__ __forceinline__ bool full(int) const { return id[K - 1] != INT_MAX; }
-  __device__ __forceinline__ int get(int t) const {
-    int r = 0;
-    #pragma unroll
-    for (int s = 0; s < K; s++) if (s == t) r = id[s];
-    return r;
-  }
-};
 
 // generic k (<= KCAP): local-memory arrays, insertion with early exit.
 constexpr int KCAP = 64;
@@ -261,10 +239,160 @@ __device__ void regularize(const double cov[6], int method, double out[6]) {
   }
 }
 
-template <typename TOPK>
+
+// ---------------------------------------------------------------------------------------------------
+// exact kNN, one WARP per query (k <= 32).
+//  * lanes 0..26 each locate one cell of the 3x3x3 block (two binary searches in parallel instead of 54
+//    in sequence); a warp scan of the cell counts gives the candidate total, which also steers the level:
+//    too many candidates -> finer level, fewer than k -> coarser, before anything is scanned;
+//  * candidates are scanned 32 at a time (coalesced), the current top-32 lives one element per lane, sorted
+//    by (distance, index); a batch in which nobody beats the k-th distance costs one ballot; otherwise the
+//    winners are inserted by shuffle (few) or the batch is bitonic-sorted and merged (many).
+// ---------------------------------------------------------------------------------------------------
+constexpr int KNN_QPW = 4;            // queries handled sequentially by one warp
+constexpr int KNN_CAND_CAP = 1024;    // prefer a finer level when the block holds more candidates than this
+
+__device__ __forceinline__ void bitonic_cmpx(float& d, int& id, int j2, bool take_min) {
+  const float od = __shfl_xor_sync(0xffffffffu, d, j2);
+  const int oi = __shfl_xor_sync(0xffffffffu, id, j2);
+  const bool other_less = cand_less(od, oi, d, id);
+  if (take_min == other_less) { d = od; id = oi; }
+}
+
+__global__ void __launch_bounds__(256)
+knn_warp_kernel(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes, int n, int k,
+                const int* __restrict__ bbox, int* __restrict__ knn_out) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const Quant qn = make_quant(bbox);
+
+  #pragma unroll 1
+  for (int qq = 0; qq < KNN_QPW; qq++) {
+    const int j = warp_global * KNN_QPW + qq;
+    if (j >= n) break;                                   // warp-uniform
+    const float4 q = __ldg(sorted + j);
+    const int self = __float_as_int(q.w);
+    unsigned ix, iy, iz;
+    quantize(qn, q.x, q.y, q.z, ix, iy, iz);
+    const double rel[3] = {(double)q.x - qn.mn[0], (double)q.y - qn.mn[1], (double)q.z - qn.mn[2]};
+
+    // start level: the level-cpl(code[j], code[j-4]) cell holds the sorted entries j-4..j (likewise on the
+    // right): the larger of the two common prefixes is a boundary-robust first guess
+    int L;
+    {
+      const unsigned long long cq = __ldg(codes + j);
+      const unsigned long long xl = cq ^ __ldg(codes + max(j - 4, 0)), xr = cq ^ __ldg(codes + min(j + 4, n - 1));
+      const int bl = (j - 4 >= 0) ? (xl ? (__clzll((long long)xl) - 1) : 63) : 0;     // codes use 63 bits
+      const int br = (j + 4 < n) ? (xr ? (__clzll((long long)xr) - 1) : 63) : 0;
+      L = min(max(bl, br) / 3, MORTON_BITS);
+    }
+
+    float td = FLT_MAX; int tid = INT_MAX;               // this lane's element of the sorted top-32
+    bool no_finer = false;
+    #pragma unroll 1
+    for (;;) {
+      const int sh = MORTON_BITS - L;
+      const int cx = (int)(ix >> sh), cy = (int)(iy >> sh), cz = (int)(iz >> sh);
+      const int ncell = 1 << L;
+      int lo = 0, cnt = 0;
+      if (lane < 27) {
+        const int oo = (lane == 0) ? 13 : (lane <= 13 ? lane - 1 : lane);   // centre cell first
+        const int nx = cx + oo % 3 - 1, ny = cy + (oo / 3) % 3 - 1, nz = cz + oo / 9 - 1;
+        if (nx >= 0 && ny >= 0 && nz >= 0 && nx < ncell && ny < ncell && nz < ncell) {
+          const unsigned long long pre = morton3((unsigned)nx, (unsigned)ny, (unsigned)nz);
+          lo = lower_bound_u64(codes, n, pre << (3 * sh));
+          const int hi = (L == 0) ? n : lower_bound_u64(codes, n, (pre + 1ull) << (3 * sh));
+          cnt = hi - lo;
+        }
+      }
+      int incl = cnt;
+      #pragma unroll
+      for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
+      const int total = __shfl_sync(FULL, incl, 31);
+      if (!no_finer && total > KNN_CAND_CAP && L < MORTON_BITS) { L++; continue; }
+      if (total < k && L > 0) { no_finer = true; L--; continue; }
+      const int excl = incl - cnt;
+
+      td = FLT_MAX; tid = INT_MAX;
+      #pragma unroll 1
+      for (int base = 0; base < total; base += 32) {
+        const int g = base + lane;
+        const bool valid = g < total;
+        // owning cell: the first lane whose inclusive count exceeds g
+        int a = 0, b = 26;
+        #pragma unroll
+        for (int s = 0; s < 5; s++) {
+          const int mid = (a + b) >> 1;
+          const int v = __shfl_sync(FULL, incl, mid);
+          if (v <= g) a = mid + 1; else b = mid;
+        }
+        a = min(a, 26);
+        const int cell_lo = __shfl_sync(FULL, lo, a), cell_ex = __shfl_sync(FULL, excl, a);
+        float d = FLT_MAX; int pid = INT_MAX;
+        if (valid) {
+          const float4 p = __ldg(sorted + cell_lo + (g - cell_ex));
+          const float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
+          d = __fmul_rn(dx, dx);
+          d = __fadd_rn(d, __fmul_rn(dy, dy));
+          d = __fadd_rn(d, __fmul_rn(dz, dz));
+          pid = __float_as_int(p.w);
+        }
+        const float kd = __shfl_sync(FULL, td, k - 1);
+        const int kid = __shfl_sync(FULL, tid, k - 1);
+        const bool pass = valid && cand_less(d, pid, kd, kid);
+        unsigned m = __ballot_sync(FULL, pass);
+        if (m == 0) continue;
+        if (__popc(m) > 6) {
+          // bitonic sort of the batch (non-passing lanes carry +inf), then bitonic merge with the top-32
+          if (!pass) { d = FLT_MAX; pid = INT_MAX; }
+          #pragma unroll
+          for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+            #pragma unroll
+            for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) bitonic_cmpx(d, pid, j2, ((lane & k2) == 0) == ((lane & j2) == 0));
+          }
+          const float rd = __shfl_sync(FULL, d, 31 - lane);
+          const int ri = __shfl_sync(FULL, pid, 31 - lane);
+          if (cand_less(rd, ri, td, tid)) { td = rd; tid = ri; }
+          #pragma unroll
+          for (int j2 = 16; j2 > 0; j2 >>= 1) bitonic_cmpx(td, tid, j2, (lane & j2) == 0);
+        } else {
+          while (m) {
+            const int srcl = __ffs(m) - 1;
+            m &= m - 1;
+            const float cd = __shfl_sync(FULL, d, srcl);
+            const int ci = __shfl_sync(FULL, pid, srcl);
+            const int pos = __popc(__ballot_sync(FULL, cand_less(td, tid, cd, ci)));   // elements that stay in front
+            const float ud = __shfl_up_sync(FULL, td, 1);
+            const int ui = __shfl_up_sync(FULL, tid, 1);
+            if (lane > pos) { td = ud; tid = ui; } else if (lane == pos) { td = cd; tid = ci; }
+          }
+        }
+      }
+      if (L == 0) break;
+      // exact iff the k-th neighbour lies inside the guaranteed-complete radius of the scanned block
+      const double sL = qn.cell * (double)(1 << sh);
+      double rs = 1e300;
+      const int cc[3] = {cx, cy, cz};
+      #pragma unroll
+      for (int dd = 0; dd < 3; dd++) {
+        if (cc[dd] - 1 >= 0) rs = fmin(rs, rel[dd] - (double)(cc[dd] - 1) * sL);
+        if (cc[dd] + 1 < ncell) rs = fmin(rs, (double)(cc[dd] + 2) * sL - rel[dd]);
+      }
+      const float kd = __shfl_sync(FULL, td, k - 1);
+      const int kid = __shfl_sync(FULL, tid, k - 1);
+      if (kid != INT_MAX && (double)kd <= rs * rs * (1.0 - 1e-6)) break;
+      no_finer = true;
+      L--;
+    }
+    if (lane < k) knn_out[(size_t)self * k + lane] = tid;
+  }
+}
+
+// generic fallback (32 < k <= 64): one thread per query, local-memory top-k
 __global__ void __launch_bounds__(128)
-knn_cov_kernel(const float4* __restrict__ pts, const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes,
-               int n, int k, int method, const int* __restrict__ bbox, float* __restrict__ cov6, int* __restrict__ knn_out) {
+knn_thread_kernel(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes, int n, int k,
+                  const int* __restrict__ bbox, int* __restrict__ knn_out) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const Quant qn = make_quant(bbox);
@@ -273,17 +401,15 @@ knn_cov_kernel(const float4* __restrict__ pts, const float4* __restrict__ sorted
   unsigned ix, iy, iz;
   quantize(qn, q.x, q.y, q.z, ix, iy, iz);
   const double rel[3] = {(double)q.x - qn.mn[0], (double)q.y - qn.mn[1], (double)q.z - qn.mn[2]};
-
-  // start level: all points between the Morton neighbours j-4 .. j+4 share this many leading octree levels
   int L;
   {
-    const unsigned long long a = codes[max(j - 4, 0)], b = codes[min(j + 4, n - 1)];
-    const unsigned long long x = a ^ b;
-    const int common_bits = x ? (__clzll((long long)x) - 1) : 63;     // codes use 63 bits
-    L = min(common_bits / 3, MORTON_BITS);
+    const unsigned long long cq = codes[j];
+    const unsigned long long xl = cq ^ codes[max(j - 4, 0)], xr = cq ^ codes[min(j + 4, n - 1)];
+    const int bl = (j - 4 >= 0) ? (xl ? (__clzll((long long)xl) - 1) : 63) : 0;
+    const int br = (j + 4 < n) ? (xr ? (__clzll((long long)xr) - 1) : 63) : 0;
+    L = min(max(bl, br) / 3, MORTON_BITS);
   }
-
-  TOPK top;
+  TopKDynamic top;
   #pragma unroll 1
   for (;; L--) {
     top.reset(k);
@@ -292,12 +418,10 @@ knn_cov_kernel(const float4* __restrict__ pts, const float4* __restrict__ sorted
     const int ncell = 1 << L;
     #pragma unroll 1
     for (int o = 0; o < 27; o++) {
-      const int oo = (o == 0) ? 13 : (o <= 13 ? o - 1 : o);   // centre cell first
-      const int nx = cx + oo % 3 - 1, ny = cy + (oo / 3) % 3 - 1, nz = cz + oo / 9 - 1;
+      const int nx = cx + o % 3 - 1, ny = cy + (o / 3) % 3 - 1, nz = cz + o / 9 - 1;
       if (nx < 0 || ny < 0 || nz < 0 || nx >= ncell || ny >= ncell || nz >= ncell) continue;
       const unsigned long long pre = morton3((unsigned)nx, (unsigned)ny, (unsigned)nz);
-      const unsigned long long klo = pre << (3 * sh);
-      const int lo = lower_bound_u64(codes, n, klo);
+      const int lo = lower_bound_u64(codes, n, pre << (3 * sh));
       const int hi = (L == 0) ? n : lower_bound_u64(codes, n, (pre + 1ull) << (3 * sh));
       for (int c = lo; c < hi; c++) {
         const float4 p = __ldg(sorted + c);
@@ -310,7 +434,6 @@ knn_cov_kernel(const float4* __restrict__ pts, const float4* __restrict__ sorted
       }
     }
     if (L == 0) break;
-    // exact iff the k-th neighbour lies inside the guaranteed-complete radius of the scanned block
     const double sL = qn.cell * (double)(1 << sh);
     double rs = 1e300;
     const int cc[3] = {cx, cy, cz};
@@ -321,17 +444,22 @@ knn_cov_kernel(const float4* __restrict__ pts, const float4* __restrict__ sorted
     }
     if (top.full(k) && (double)top.worst(k) <= rs * rs * (1.0 - 1e-6)) break;
   }
+  for (int t = 0; t < k; t++) knn_out[(size_t)self * k + t] = top.get(t);
+}
 
-  if (knn_out) for (int t = 0; t < k; t++) knn_out[(size_t)self * k + t] = top.get(t);
-  if (!cov6) return;
-
-  // mean-centred scatter / k, neighbours in (distance, index) order (rot_vgicp_impl.hpp:438-456)
+// mean-centred scatter / k over the neighbours in (distance, index) order, then the regulariser
+// (rot_vgicp_impl.hpp:438-492). One thread per point.
+__global__ void __launch_bounds__(128)
+cov_from_knn_kernel(const float4* __restrict__ pts, const int* __restrict__ knn, int n, int k, int method, float* __restrict__ cov6) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int* row = knn + (size_t)i * k;
   double sx = 0, sy = 0, sz = 0;
-  for (int t = 0; t < k; t++) { const float4 p = __ldg(pts + top.get(t)); sx += (double)p.x; sy += (double)p.y; sz += (double)p.z; }
+  for (int t = 0; t < k; t++) { const float4 p = __ldg(pts + __ldg(row + t)); sx += (double)p.x; sy += (double)p.y; sz += (double)p.z; }
   const double mx = sx / k, my = sy / k, mz = sz / k;
   double c[6] = {0, 0, 0, 0, 0, 0};
   for (int t = 0; t < k; t++) {
-    const float4 p = __ldg(pts + top.get(t));
+    const float4 p = __ldg(pts + __ldg(row + t));
     const double dx = (double)p.x - mx, dy = (double)p.y - my, dz = (double)p.z - mz;
     c[0] += dx * dx; c[1] += dx * dy; c[2] += dx * dz; c[3] += dy * dy; c[4] += dy * dz; c[5] += dz * dz;
   }
@@ -339,7 +467,7 @@ knn_cov_kernel(const float4* __restrict__ pts, const float4* __restrict__ sorted
   for (int t = 0; t < 6; t++) c[t] /= (double)k;
   double out[6];
   regularize(c, method, out);
-  const size_t base = (size_t)(self / TILE_PTS) * COV_PLANES * TILE_PTS + (self % TILE_PTS);
+  const size_t base = (size_t)(i / TILE_PTS) * COV_PLANES * TILE_PTS + (i % TILE_PTS);
   #pragma unroll
   for (int t = 0; t < 6; t++) cov6[base + (size_t)t * TILE_PTS] = (float)out[t];
 }
@@ -355,21 +483,24 @@ size_t cov_cub_temp_bytes(int n) {
 
 cudaError_t launch_covariances(const CovLaunch& L, cudaStream_t stream) {
   if (L.n <= 0) return cudaSuccess;
-  if (L.k > KCAP || L.k < 1 || L.n < L.k) return cudaErrorInvalidValue;
+  if (L.k > KCAP || L.k < 1 || L.n < L.k || !L.knn) return cudaErrorInvalidValue;
   const int n = L.n;
   const int tb = 256, nb = (n + tb - 1) / tb;
   bbox_init_kernel<<<1, 32, 0, stream>>>(L.s.bbox);
-  bbox_kernel<<<min(nb, 592), tb, 0, stream>>>(L.pts, n, L.s.bbox);
+  bbox_kernel<<<min(nb, 148), tb, 0, stream>>>(L.pts, n, L.s.bbox);
   morton_kernel<<<nb, tb, 0, stream>>>(L.pts, n, L.s.bbox, L.s.codes_in, L.s.idx_in);
   size_t temp = L.s.cub_temp_bytes;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(L.s.cub_temp, temp, L.s.codes_in, L.s.codes_out, L.s.idx_in, L.s.idx_out, n, 0,
                                                   3 * MORTON_BITS, stream);
   if (e != cudaSuccess) return e;
   gather_sorted_kernel<<<nb, tb, 0, stream>>>(L.pts, L.s.idx_out, n, L.s.sorted);
-  const int kb = (n + 127) / 128;
-  if (L.k == 20) knn_cov_kernel<TopKStatic<20>><<<kb, 128, 0, stream>>>(L.pts, L.s.sorted, L.s.codes_out, n, L.k, L.method, L.s.bbox, L.cov6, L.knn_out);
-  else if (L.k == 10) knn_cov_kernel<TopKStatic<10>><<<kb, 128, 0, stream>>>(L.pts, L.s.sorted, L.s.codes_out, n, L.k, L.method, L.s.bbox, L.cov6, L.knn_out);
-  else knn_cov_kernel<TopKDynamic><<<kb, 128, 0, stream>>>(L.pts, L.s.sorted, L.s.codes_out, n, L.k, L.method, L.s.bbox, L.cov6, L.knn_out);
+  if (L.k <= 32) {
+    const int queries_per_block = (256 / 32) * KNN_QPW;
+    knn_warp_kernel<<<(n + queries_per_block - 1) / queries_per_block, 256, 0, stream>>>(L.s.sorted, L.s.codes_out, n, L.k, L.s.bbox, L.knn);
+  } else {
+    knn_thread_kernel<<<(n + 127) / 128, 128, 0, stream>>>(L.s.sorted, L.s.codes_out, n, L.k, L.s.bbox, L.knn);
+  }
+  if (L.cov6) cov_from_knn_kernel<<<(n + 127) / 128, 128, 0, stream>>>(L.pts, L.knn, n, L.k, L.method, L.cov6);
   return cudaGetLastError();
 }
 

@@ -23,7 +23,7 @@ struct CovLaunch {
   int k;                      // neighbours incl. self (k_correspondences_)
   int method;                 // RG_REG_*
   float* cov6;                // out, tile-planar (may be null when only knn_out is wanted)
-  int* knn_out;               // optional [n*k] original indices sorted by (distance, index); may be null
+  int* knn;                   // [n*k] neighbour indices (original numbering) sorted by (distance, index): scratch + test output
   CovScratch s;
 };
 

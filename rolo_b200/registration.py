@@ -228,6 +228,7 @@ class RotVGICP:
         return out
 
     def lastKernelUs(self): return self._L.rg_last_kernel_us(self._h)
+    def stream(self): return self._L.rg_stream(self._h)
 
     def setReduceHook(self, fn, on_device: bool):
         """Sharded registration (config 4): fn(buf_ptr:int, count:int, on_device:bool, stream:int) -> int."""
@@ -276,5 +277,6 @@ class RotVGICPBatch:
             p._final = out[i]
         return out
 
+    def stream(self): return self._L.rg_batch_stream(self._h)
     def lastLinearizeUs(self): return self._L.rg_batch_last_linearize_us(self._h)
     def lastLinearizeLaunches(self): return self._L.rg_batch_last_linearize_launches(self._h)

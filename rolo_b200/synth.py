@@ -157,3 +157,46 @@ def pose_error(T_a: np.ndarray, T_b: np.ndarray) -> tuple[float, float]:
     D = np.linalg.inv(T_a) @ T_b
     c = np.clip((np.trace(D[:3, :3]) - 1.0) / 2.0, -1.0, 1.0)
     return float(np.arccos(c)), float(np.linalg.norm(T_a[:3, 3] - T_b[:3, 3]))
+
+
+# ---- torch variants (used by bench.py to build many full-size scans quickly on the GPU) --------------
+def scan_torch(scene: dict, T_ws: np.ndarray, sensor: str = "os1-128", sigma: float = 0.02, seed: int = 1234, device="cuda"):
+    """Same geometry as scan(), evaluated with torch in fp64 on `device`; noise from a torch generator.
+    Returns a float32 (N,4) tensor on `device` (w = 1). Not bit-identical to scan() (different RNG)."""
+    import torch
+    d_np, _, _ = ray_dirs(sensor)
+    dt = torch.float64
+    d_s = torch.as_tensor(d_np, dtype=dt, device=device)
+    R = torch.as_tensor(T_ws[:3, :3], dtype=dt, device=device)
+    o = torch.as_tensor(T_ws[:3, 3], dtype=dt, device=device)
+    d = d_s @ R.T
+    inf = torch.tensor(float("inf"), dtype=dt, device=device)
+
+    def slab(bmin, bmax):
+        bmin = torch.as_tensor(bmin, dtype=dt, device=device); bmax = torch.as_tensor(bmax, dtype=dt, device=device)
+        inv = 1.0 / d
+        t0 = (bmin - o) * inv; t1 = (bmax - o) * inv
+        tn = torch.minimum(t0, t1); tf = torch.maximum(t0, t1)
+        tn = torch.where(torch.isnan(tn), -inf, tn); tf = torch.where(torch.isnan(tf), inf, tf)
+        return tn.max(dim=1).values, tf.min(dim=1).values
+
+    _, t = slab(ROOM_MIN, ROOM_MAX)
+    for bmin, bmax in scene["boxes"]:
+        tn, tf2 = slab(bmin, bmax)
+        hit = (tn <= tf2) & (tn > 1e-6) & (tn < t)
+        t = torch.where(hit, tn, t)
+    r = scene["cyl_r"]
+    a = d[:, 0] ** 2 + d[:, 1] ** 2
+    for c in scene["cylinders"]:
+        oc0 = float(T_ws[0, 3] - c[0]); oc1 = float(T_ws[1, 3] - c[1])
+        b = 2.0 * (d[:, 0] * oc0 + d[:, 1] * oc1)
+        cc = oc0 * oc0 + oc1 * oc1 - r * r
+        disc = b * b - 4.0 * a * cc
+        tc = (-b - torch.sqrt(torch.clamp(disc, min=0.0))) / (2.0 * a)
+        hit = (disc > 0) & (a > 1e-12) & (tc > 1e-6) & (tc < t)
+        t = torch.where(hit, tc, t)
+    g = torch.Generator(device=device); g.manual_seed(int(seed))
+    t = t + sigma * torch.randn(t.shape, dtype=dt, device=device, generator=g)
+    pts = torch.ones((d_s.shape[0], 4), dtype=torch.float32, device=device)
+    pts[:, :3] = (d_s * t[:, None]).to(torch.float32)
+    return pts
