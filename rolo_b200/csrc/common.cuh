@@ -92,24 +92,27 @@ __device__ __forceinline__ void voxel_coord_exact(const GridParams& g, double x,
 // back to the exact fp64 evaluation when the value lies within a conservative error bound of a cell
 // boundary. The returned coordinate always equals voxel_coord_exact().
 // Error budgets (absolute, before dividing by the resolution):
-//   theta: fp32 inputs (6e-8 rel) + atan2f (<=2 ulp of pi = 4.8e-7)      -> 1.5e-6 rad
+//   theta: fp32 inputs (6e-8 rel) + atan2f (<=2 ulp of pi = 4.8e-7) + fp32 pi/add -> 2.0e-6 rad
 //   phi  : u = z/r (3e-7 abs) * 1/sqrt(1-u^2) (<= 2.3 for |u|<=0.9) + acosf (2 ulp) -> 4e-6 rad; |u|>0.9 -> exact
 //   r    : sqrtf chain 4e-7 relative
 __device__ __forceinline__ void voxel_coord(const GridParams& g, double x, double y, double z, int& cx, int& cy, int& cz) {
   if (g.voxel_type == 0) {
+    // everything in fp32; the margins include the fp32 rounding of the final scale (|value| * 2^-22)
     const float xf = (float)x, yf = (float)y, zf = (float)z;
     const float r2 = xf * xf + yf * yf + zf * zf;
     const float rf = sqrtf(r2);
     const float u = zf / rf;
-    const double th = ((double)atan2f(yf, xf) + 3.14159265358979323846) * g.inv_res[0];
-    const double ph = (double)acosf(u) * g.inv_res[1];
-    const double rr = (double)rf * g.inv_res[2];
-    const double fth = floor(th), fph = floor(ph), frr = floor(rr);
-    const double dth = 1.5e-6 * g.inv_res[0] + 1e-9 * th;
-    const double dph = 4.0e-6 * g.inv_res[1] + 1e-9 * ph;
-    const double drr = 4.0e-7 * rr + 1e-9;
-    bool safe = (th - fth > dth) && (fth + 1.0 - th > dth) && (ph - fph > dph) && (fph + 1.0 - ph > dph) &&
-                (rr - frr > drr) && (frr + 1.0 - rr > drr) && (fabsf(u) <= 0.9f) && (rf > 1e-3f) && (rf < 1e6f);
+    const float ir0 = (float)g.inv_res[0], ir1 = (float)g.inv_res[1], ir2 = (float)g.inv_res[2];
+    const float th = (atan2f(yf, xf) + 3.14159274f) * ir0;
+    const float ph = acosf(u) * ir1;
+    const float rr = rf * ir2;
+    const float fth = floorf(th), fph = floorf(ph), frr = floorf(rr);
+    const float dth = 2.0e-6f * ir0 + 4e-7f * th;
+    const float dph = 4.0e-6f * ir1 + 4e-7f * ph;
+    const float drr = 8.0e-7f * rr + 1e-9f;
+    bool safe = (th - fth > dth) && (fth + 1.0f - th > dth) && (ph - fph > dph) && (fph + 1.0f - ph > dph) &&
+                (rr - frr > drr) && (frr + 1.0f - rr > drr) && (fabsf(u) <= 0.9f) && (rf > 1e-3f) && (rf < 1e6f) &&
+                (th < 1e6f) && (ph < 1e6f) && (rr < 1e6f);
     if (safe) { cx = (int)fth; cy = (int)fph; cz = (int)frr; }
     else voxel_coord_exact(g, x, y, z, cx, cy, cz);
   } else {

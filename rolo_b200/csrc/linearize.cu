@@ -10,7 +10,8 @@
 // warp shuffles -> shared memory -> per-CTA partial -> last-CTA fixed-order final pass (deterministic).
 //
 // Data movement: source points (float4) and covariances (tile-planar 6 x fp32) stream through shared
-// memory as 4 KB + 6 KB tiles with 1-D TMA bulk copies (cp.async.bulk + mbarrier, double-buffered);
+// memory as 4 KB + 6 KB tiles with 1-D TMA bulk copies (cp.async.bulk + full/empty mbarrier ring, 4 stages,
+// no CTA-wide barrier in the main loop);
 // the voxel table/payload gathers go through the read-only path (L1/L2 resident). All arithmetic
 // that decides a voxel or enters a sum is fp64 (fp32 is only a pre-filter for the key).
 // No tensor cores: there is no dense contraction in this path.
@@ -24,6 +25,7 @@ namespace {
 
 constexpr int NTHREADS = TILE_PTS;               // 256
 constexpr int NWARPS = NTHREADS / 32;
+constexpr int NSTAGES = 4;                       // TMA ring depth (4 x 10 KB per CTA)
 constexpr uint32_t PTS_TILE_BYTES = TILE_PTS * sizeof(float4);             // 4096
 constexpr uint32_t COV_TILE_BYTES = TILE_PTS * COV_PLANES * sizeof(float); // 6144
 
@@ -34,6 +36,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -75,14 +80,16 @@ template <int MODE, bool REFRESH, int NOFF>
 __global__ void __launch_bounds__(NTHREADS, 2)
 linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict__ dyn_arr, const __grid_constant__ LinDyn dyn0, int blocks_per_pair) {
   constexpr int NACC = AccN<MODE>::value;
-  __shared__ __align__(128) float4 s_pts[2][TILE_PTS];
-  __shared__ __align__(128) float s_cov[2][COV_PLANES * TILE_PTS];
-  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ __align__(128) float4 s_pts[NSTAGES][TILE_PTS];
+  __shared__ __align__(128) float s_cov[NSTAGES][COV_PLANES * TILE_PTS];
+  __shared__ __align__(8) uint64_t s_full[NSTAGES];    // TMA bytes landed
+  __shared__ __align__(8) uint64_t s_empty[NSTAGES];   // every warp has copied its operands out of the stage
   __shared__ LinDyn s_dyn;
   __shared__ double s_red[NWARPS][RES_USED];
   __shared__ int s_is_last;
 
   const int tid = threadIdx.x;
+  const int lane = tid & 31;
   const int pair = blockIdx.y;
   const int blk = blockIdx.x;
   const LinStatic& st = st_arr[pair];
@@ -93,7 +100,11 @@ linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict_
     double* dst = reinterpret_cast<double*>(&s_dyn);
     for (int k = tid; k < (int)(sizeof(LinDyn) / sizeof(double)); k += NTHREADS) dst[k] = src[k];
   }
-  if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); fence_mbar_init(); }
+  if (tid == 0) {
+    #pragma unroll
+    for (int sidx = 0; sidx < NSTAGES; sidx++) { mbar_init(&s_full[sidx], 1); mbar_init(&s_empty[sidx], NWARPS); }
+    fence_mbar_init();
+  }
   __syncthreads();
 
   const int n = st.n;
@@ -109,27 +120,35 @@ linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict_
   #pragma unroll
   for (int k = 0; k < NACC; k++) acc[k] = 0.0;
 
-  // prologue: first tile of this CTA
-  if (tid == 0 && blk < ntiles) {
-    mbar_arrive_expect_tx(&s_bar[0], PTS_TILE_BYTES + COV_TILE_BYTES);
-    tma_load_1d(&s_pts[0][0], g_pts + (size_t)blk * TILE_PTS, PTS_TILE_BYTES, &s_bar[0]);
-    tma_load_1d(&s_cov[0][0], g_cov + (size_t)blk * COV_PLANES * TILE_PTS, COV_TILE_BYTES, &s_bar[0]);
+  // prologue: fill the ring (TMA 1-D bulk copies, one elected thread)
+  if (tid == 0) {
+    #pragma unroll
+    for (int sidx = 0; sidx < NSTAGES; sidx++) {
+      const int tl = blk + sidx * blocks_per_pair;
+      if (tl < ntiles) {
+        mbar_arrive_expect_tx(&s_full[sidx], PTS_TILE_BYTES + COV_TILE_BYTES);
+        tma_load_1d(&s_pts[sidx][0], g_pts + (size_t)tl * TILE_PTS, PTS_TILE_BYTES, &s_full[sidx]);
+        tma_load_1d(&s_cov[sidx][0], g_cov + (size_t)tl * COV_PLANES * TILE_PTS, COV_TILE_BYTES, &s_full[sidx]);
+      }
+    }
   }
 
   int it = 0;
   for (int tile = blk; tile < ntiles; tile += blocks_per_pair, it++) {
-    const int stage = it & 1;
-    const int next = tile + blocks_per_pair;
-    if (tid == 0 && next < ntiles) {   // prefetch the next tile into the other buffer (freed by the trailing __syncthreads)
-      mbar_arrive_expect_tx(&s_bar[stage ^ 1], PTS_TILE_BYTES + COV_TILE_BYTES);
-      tma_load_1d(&s_pts[stage ^ 1][0], g_pts + (size_t)next * TILE_PTS, PTS_TILE_BYTES, &s_bar[stage ^ 1]);
-      tma_load_1d(&s_cov[stage ^ 1][0], g_cov + (size_t)next * COV_PLANES * TILE_PTS, COV_TILE_BYTES, &s_bar[stage ^ 1]);
-    }
-    mbar_wait(&s_bar[stage], (it >> 1) & 1);
+    const int stage = it % NSTAGES;
+    const uint32_t phase = (uint32_t)(it / NSTAGES) & 1u;
+    mbar_wait(&s_full[stage], phase);
+
+    // copy this thread's operands out of the stage, then hand the stage back to the producer: no CTA-wide barrier
+    const float4 pf = s_pts[stage][tid];
+    const float* cv = &s_cov[stage][tid];
+    const float af0 = cv[0 * TILE_PTS], af1 = cv[1 * TILE_PTS], af2 = cv[2 * TILE_PTS];
+    const float af3 = cv[3 * TILE_PTS], af4 = cv[4 * TILE_PTS], af5 = cv[5 * TILE_PTS];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s_empty[stage]);
 
     const int i = tile * TILE_PTS + tid;
     if (i < n) {
-      const float4 pf = s_pts[stage][tid];
       const double px = (double)pf.x, py = (double)pf.y, pz = (double)pf.z;
       // p' = R p + t
       const double x = s_dyn.R[0] * px + s_dyn.R[1] * py + s_dyn.R[2] * pz + s_dyn.t[0];
@@ -137,43 +156,69 @@ linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict_
       const double z = s_dyn.R[6] * px + s_dyn.R[7] * py + s_dyn.R[8] * pz + s_dyn.t[2];
 
       int cx = 0, cy = 0, cz = 0;
-      if (REFRESH) voxel_coord(st.grid, x, y, z, cx, cy, cz);
+      ulonglong2 slot0 = make_ulonglong2(KEY_EMPTY, 0ull);
+      unsigned h0 = 0;
+      bool key_ok = false;
+      if (REFRESH) {
+        voxel_coord(st.grid, x, y, z, cx, cy, cz);
+        // issue the first probe (offset 0) now; it is consumed after C_A has been computed
+        int dx0, dy0, dz0;
+        neighbor_offset<NOFF>(0, dx0, dy0, dz0);
+        key_ok = key_in_range(cx + dx0, cy + dy0, cz + dz0);
+        if (key_ok) { h0 = hash_key(pack_key(cx + dx0, cy + dy0, cz + dz0)) & mask; slot0 = __ldg(reinterpret_cast<const ulonglong2*>(table + h0)); }
+      } else if (NOFF == 1) {
+        slot0.y = (unsigned long long)(unsigned)corr[i];
+      }
 
-      // C_A = Rm A Rm^T (symmetric), computed lazily on the first hit
-      double ca0 = 0, ca1 = 0, ca2 = 0, ca3 = 0, ca4 = 0, ca5 = 0;
-      bool have_ca = false;
+      // C_A = Rm A Rm^T (symmetric): independent of the lookup, overlaps the table probe latency
+      double ca0, ca1, ca2, ca3, ca4, ca5;
+      {
+        const double a0 = (double)af0, a1 = (double)af1, a2 = (double)af2, a3 = (double)af3, a4 = (double)af4, a5 = (double)af5;
+        const double r0 = s_dyn.Rm[0], r1 = s_dyn.Rm[1], r2 = s_dyn.Rm[2];
+        const double r3 = s_dyn.Rm[3], r4 = s_dyn.Rm[4], r5 = s_dyn.Rm[5];
+        const double r6 = s_dyn.Rm[6], r7 = s_dyn.Rm[7], r8 = s_dyn.Rm[8];
+        const double t00 = r0 * a0 + r1 * a1 + r2 * a2, t01 = r0 * a1 + r1 * a3 + r2 * a4, t02 = r0 * a2 + r1 * a4 + r2 * a5;
+        const double t10 = r3 * a0 + r4 * a1 + r5 * a2, t11 = r3 * a1 + r4 * a3 + r5 * a4, t12 = r3 * a2 + r4 * a4 + r5 * a5;
+        const double t20 = r6 * a0 + r7 * a1 + r8 * a2, t21 = r6 * a1 + r7 * a3 + r8 * a4, t22 = r6 * a2 + r7 * a4 + r8 * a5;
+        ca0 = t00 * r0 + t01 * r1 + t02 * r2;
+        ca1 = t00 * r3 + t01 * r4 + t02 * r5;
+        ca2 = t00 * r6 + t01 * r7 + t02 * r8;
+        ca3 = t10 * r3 + t11 * r4 + t12 * r5;
+        ca4 = t10 * r6 + t11 * r7 + t12 * r8;
+        ca5 = t20 * r6 + t21 * r7 + t22 * r8;
+      }
 
       #pragma unroll 1
       for (int o = 0; o < NOFF; o++) {
         int id;
         if (REFRESH) {
-          int dx, dy, dz;
-          neighbor_offset<NOFF>(o, dx, dy, dz);
-          id = table_lookup(table, mask, cx + dx, cy + dy, cz + dz);
+          if (o == 0) {
+            // resolve the pre-issued probe (vmp_voxel.hpp:226-233); continue probing linearly on a collision
+            id = -1;
+            if (key_ok) {
+              int dx0, dy0, dz0;
+              neighbor_offset<NOFF>(0, dx0, dy0, dz0);
+              const unsigned long long key = pack_key(cx + dx0, cy + dy0, cz + dz0);
+              ulonglong2 sl = slot0;
+              unsigned h = h0;
+              #pragma unroll 1
+              for (unsigned probe = 0; probe <= mask; probe++) {
+                if (sl.x == key) { id = (int)(unsigned)(sl.y & 0xFFFFFFFFull); break; }
+                if (sl.x == KEY_EMPTY) break;
+                h = (h + 1) & mask;
+                sl = __ldg(reinterpret_cast<const ulonglong2*>(table + h));
+              }
+            }
+          } else {
+            int dx, dy, dz;
+            neighbor_offset<NOFF>(o, dx, dy, dz);
+            id = table_lookup(table, mask, cx + dx, cy + dy, cz + dz);
+          }
           corr[(size_t)i * NOFF + o] = id;
         } else {
-          id = corr[(size_t)i * NOFF + o];
+          id = (NOFF == 1) ? (int)(unsigned)slot0.y : corr[(size_t)i * NOFF + o];
         }
         if (id < 0) continue;
-
-        if (!have_ca) {
-          have_ca = true;
-          const float* cv = &s_cov[stage][tid];
-          const double a0 = (double)cv[0 * TILE_PTS], a1 = (double)cv[1 * TILE_PTS], a2 = (double)cv[2 * TILE_PTS];
-          const double a3 = (double)cv[3 * TILE_PTS], a4 = (double)cv[4 * TILE_PTS], a5 = (double)cv[5 * TILE_PTS];
-          const double r0 = s_dyn.Rm[0], r1 = s_dyn.Rm[1], r2 = s_dyn.Rm[2];
-          const double r3 = s_dyn.Rm[3], r4 = s_dyn.Rm[4], r5 = s_dyn.Rm[5];
-          const double r6 = s_dyn.Rm[6], r7 = s_dyn.Rm[7], r8 = s_dyn.Rm[8];
-          const double t00 = r0 * a0 + r1 * a1 + r2 * a2, t01 = r0 * a1 + r1 * a3 + r2 * a4, t02 = r0 * a2 + r1 * a4 + r2 * a5;
-          const double t10 = r3 * a0 + r4 * a1 + r5 * a2, t11 = r3 * a1 + r4 * a3 + r5 * a4, t12 = r3 * a2 + r4 * a4 + r5 * a5;
-          const double t20 = r6 * a0 + r7 * a1 + r8 * a2, t21 = r6 * a1 + r7 * a3 + r8 * a4, t22 = r6 * a2 + r7 * a4 + r8 * a5;
-          ca0 = t00 * r0 + t01 * r1 + t02 * r2;
-          ca1 = t00 * r3 + t01 * r4 + t02 * r5;
-          ca2 = t00 * r6 + t01 * r7 + t02 * r8;
-          ca3 = t10 * r3 + t11 * r4 + t12 * r5;
-          ca4 = t10 * r6 + t11 * r7 + t12 * r8;
-          ca5 = t20 * r6 + t21 * r7 + t22 * r8;
-        }
 
         // voxel payload gather: 80 B as 5 x 16 B read-only loads
         const double2* vp = reinterpret_cast<const double2*>(vox + id);
@@ -245,11 +290,20 @@ linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict_
         }
       }
     }
-    __syncthreads();   // every thread is done with buffer `stage` before it is refilled
+    // producer: refill this stage with the tile NSTAGES iterations ahead once every warp has released it
+    if (tid == 0) {
+      const int tl = tile + NSTAGES * blocks_per_pair;
+      if (tl < ntiles) {
+        mbar_wait(&s_empty[stage], phase);
+        mbar_arrive_expect_tx(&s_full[stage], PTS_TILE_BYTES + COV_TILE_BYTES);
+        tma_load_1d(&s_pts[stage][0], g_pts + (size_t)tl * TILE_PTS, PTS_TILE_BYTES, &s_full[stage]);
+        tma_load_1d(&s_cov[stage][0], g_cov + (size_t)tl * COV_PLANES * TILE_PTS, COV_TILE_BYTES, &s_full[stage]);
+      }
+    }
   }
 
   // ---- reduction: warp shuffle tree -> shared -> CTA partial -> last-CTA final pass ---------------
-  const int lane = tid & 31, warp = tid >> 5;
+  const int warp = tid >> 5;
   #pragma unroll
   for (int k = 0; k < NACC; k++) {
     const double v = warp_sum(acc[k]);
