@@ -230,3 +230,33 @@ def ldlt_solve(A, b):
     A = np.ascontiguousarray(A, dtype=np.float64); b = np.ascontiguousarray(b, dtype=np.float64)
     x = np.empty_like(b)
     lib().ro_ldlt_solve(_d(A), _d(b), C.c_int(b.shape[0]), _d(x)); return x
+
+
+# ---- upstream range-image passes (oracle/frontend_oracle.cpp) ---------------------------------------
+def image_projection(raw: np.ndarray, n_scan, horizon, downsample_rate=1, min_range=2.0, max_range=1000.0, ring_offset=20):
+    L = lib()
+    raw = np.ascontiguousarray(raw)
+    cells = n_scan * horizon
+    rim = np.empty((n_scan, horizon), dtype=np.float32)
+    ext = np.empty((cells, 4), dtype=np.float32); col = np.empty(cells, dtype=np.int32); rng = np.empty(cells, dtype=np.float32)
+    st = np.empty(n_scan, dtype=np.int32); en = np.empty(n_scan, dtype=np.int32)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    n = L.ro_image_projection(vp(raw), C.c_size_t(raw.shape[0]), C.c_int(raw.dtype.itemsize), C.c_int(ring_offset), C.c_int(n_scan), C.c_int(horizon),
+                              C.c_int(downsample_rate), C.c_float(min_range), C.c_float(max_range), vp(rim), vp(ext), vp(col), vp(rng), vp(st), vp(en))
+    return {"range_image": rim, "extracted": ext[:n].copy(), "point_col_ind": col[:n].copy(), "point_range": rng[:n].copy(),
+            "start_ring_index": st, "end_ring_index": en, "n": n}
+
+
+def feature_extraction(proj: dict, n_scan, horizon, edge_threshold=0.8, surf_threshold=0.1, surf_leaf_size=0.4):
+    L = lib()
+    n = proj["n"]
+    ext = np.ascontiguousarray(proj["extracted"], dtype=np.float32); col = np.ascontiguousarray(proj["point_col_ind"], dtype=np.int32)
+    rng = np.ascontiguousarray(proj["point_range"], dtype=np.float32)
+    st = np.ascontiguousarray(proj["start_ring_index"], dtype=np.int32); en = np.ascontiguousarray(proj["end_ring_index"], dtype=np.int32)
+    curv = np.empty(n, dtype=np.float32); picked = np.empty(n, dtype=np.int32); label = np.empty(n, dtype=np.int32)
+    corner = np.empty((n_scan * 120, 4), dtype=np.float32); surf = np.empty((n_scan * horizon, 4), dtype=np.float32)
+    nc = C.c_int(); ns = C.c_int()
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    L.ro_feature_extraction(vp(ext), vp(col), vp(rng), vp(st), vp(en), C.c_int(n), C.c_int(n_scan), C.c_int(horizon), C.c_float(edge_threshold),
+                            C.c_float(surf_threshold), C.c_float(surf_leaf_size), vp(curv), vp(picked), vp(label), vp(corner), C.byref(nc), vp(surf), C.byref(ns))
+    return {"curvature": curv, "neighbor_picked": picked, "label": label, "corner": corner[:nc.value].copy(), "surface": surf[:ns.value].copy()}

@@ -251,6 +251,12 @@ struct rg_ctx {
 
   rg_reduce_fn reduce_fn = nullptr; void* reduce_user = nullptr; int reduce_on_device = 0;
 
+  // front end (range-image projection + feature extraction) scratch
+  DevBuf<unsigned char> fe_raw;
+  DevBuf<int> fe_owner, fe_row_count, fe_col, fe_start, fe_end, fe_counts, fe_picked, fe_label, fe_corner_cnt, fe_surf_cnt;
+  DevBuf<float> fe_range_image, fe_prange, fe_curv;
+  DevBuf<float4> fe_full, fe_extracted, fe_corner_ring, fe_surf_ring, fe_corner_out, fe_surf_out;
+
   rg_batch* batch = nullptr;            // non-null when owned by a batch
   int batch_index = 0;
 };
@@ -648,6 +654,10 @@ void rg_destroy(rg_ctx* c) {
   c->src.release(); c->tgt.release();
   c->table.release(); c->vox.release(); c->sums.release(); c->slot_of_point.release(); c->counters.release();
   c->codes_in.release(); c->codes_out.release(); c->idx_in.release(); c->idx_out.release(); c->bbox.release(); c->sorted.release(); c->cub_temp.release(); c->knn_idx.release();
+  c->fe_raw.release(); c->fe_owner.release(); c->fe_row_count.release(); c->fe_col.release(); c->fe_start.release(); c->fe_end.release();
+  c->fe_counts.release(); c->fe_picked.release(); c->fe_label.release(); c->fe_corner_cnt.release(); c->fe_surf_cnt.release();
+  c->fe_range_image.release(); c->fe_prange.release(); c->fe_curv.release(); c->fe_full.release(); c->fe_extracted.release();
+  c->fe_corner_ring.release(); c->fe_surf_ring.release(); c->fe_corner_out.release(); c->fe_surf_out.release();
   c->corr.release(); c->partials.release(); c->counter.release(); c->result_dev.release(); c->st_dev.release(); c->staging.release();
   if (c->result_host) pool().pinned_free(c->result_host);
   if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1081,6 +1091,100 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
     if (c->lsq.failed) rc_all = RG_ERR_NOT_CONVERGED;
   }
   return rc_all;
+}
+
+// ------------------------------------------------------------------------------------------------
+// upstream range-image passes
+// ------------------------------------------------------------------------------------------------
+static int fe_alloc(rg_ctx* c, int n_scan, int horizon) {
+  const size_t cells = (size_t)n_scan * horizon;
+  RG_CUDA(c, c->fe_owner.ensure(c->device, cells)); RG_CUDA(c, c->fe_range_image.ensure(c->device, cells));
+  RG_CUDA(c, c->fe_full.ensure(c->device, cells)); RG_CUDA(c, c->fe_row_count.ensure(c->device, n_scan));
+  RG_CUDA(c, c->fe_extracted.ensure(c->device, cells)); RG_CUDA(c, c->fe_col.ensure(c->device, cells));
+  RG_CUDA(c, c->fe_prange.ensure(c->device, cells)); RG_CUDA(c, c->fe_start.ensure(c->device, n_scan)); RG_CUDA(c, c->fe_end.ensure(c->device, n_scan));
+  RG_CUDA(c, c->fe_counts.ensure(c->device, 8));
+  RG_CUDA(c, c->fe_curv.ensure(c->device, cells)); RG_CUDA(c, c->fe_picked.ensure(c->device, cells)); RG_CUDA(c, c->fe_label.ensure(c->device, cells));
+  RG_CUDA(c, c->fe_corner_ring.ensure(c->device, (size_t)n_scan * FE_MAX_CORNERS_PER_RING)); RG_CUDA(c, c->fe_corner_cnt.ensure(c->device, n_scan));
+  RG_CUDA(c, c->fe_surf_ring.ensure(c->device, cells)); RG_CUDA(c, c->fe_surf_cnt.ensure(c->device, n_scan));
+  RG_CUDA(c, c->fe_corner_out.ensure(c->device, (size_t)n_scan * FE_MAX_CORNERS_PER_RING)); RG_CUDA(c, c->fe_surf_out.ensure(c->device, cells));
+  return RG_OK;
+}
+
+int rg_image_projection(rg_ctx* c, const void* raw, size_t n_points, const rg_projection_params* p, float* range_image, float* extracted,
+                        int32_t* col_ind, float* point_range, int32_t* start_ring, int32_t* end_ring, int32_t* n_extracted) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (!p || (!raw && n_points) || !n_extracted) return set_err(c, RG_ERR_INVALID, "rg_image_projection: null argument");
+  if (p->n_scan < 1 || p->horizon_scan < 1 || p->downsample_rate < 1 || p->point_stride_bytes < 12 || p->point_stride_bytes % 4 ||
+      p->ring_offset_bytes < 0 || p->ring_offset_bytes + 2 > p->point_stride_bytes || n_points > (size_t)INT32_MAX / 2)
+    return set_err(c, RG_ERR_INVALID, "rg_image_projection: bad parameters");
+  if (int rc = fe_alloc(c, p->n_scan, p->horizon_scan)) return rc;
+  const size_t cells = (size_t)p->n_scan * p->horizon_scan;
+  RG_CUDA(c, c->fe_raw.ensure(c->device, std::max<size_t>(n_points * p->point_stride_bytes, 16)));
+  if (n_points) RG_CUDA(c, cudaMemcpyAsync(c->fe_raw.p, raw, n_points * p->point_stride_bytes, cudaMemcpyHostToDevice, c->stream));
+  ProjLaunch L;
+  L.raw = c->fe_raw.p; L.n_points = (int)n_points; L.stride = p->point_stride_bytes; L.ring_offset = p->ring_offset_bytes;
+  L.n_scan = p->n_scan; L.horizon = p->horizon_scan; L.downsample = p->downsample_rate; L.min_range = p->lidar_min_range; L.max_range = p->lidar_max_range;
+  L.owner = c->fe_owner.p; L.range_image = c->fe_range_image.p; L.full = c->fe_full.p; L.row_count = c->fe_row_count.p;
+  L.extracted = c->fe_extracted.p; L.col_ind = c->fe_col.p; L.point_range = c->fe_prange.p; L.start_ring = c->fe_start.p; L.end_ring = c->fe_end.p;
+  L.n_extracted = c->fe_counts.p;
+  RG_CUDA(c, launch_projection(L, c->stream));
+  g_launches += 5;
+  int n = 0;
+  RG_CUDA(c, cudaMemcpyAsync(&n, c->fe_counts.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  *n_extracted = n;
+  if (range_image) RG_CUDA(c, cudaMemcpyAsync(range_image, c->fe_range_image.p, cells * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (start_ring) RG_CUDA(c, cudaMemcpyAsync(start_ring, c->fe_start.p, p->n_scan * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (end_ring) RG_CUDA(c, cudaMemcpyAsync(end_ring, c->fe_end.p, p->n_scan * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (n > 0) {
+    if (extracted) RG_CUDA(c, cudaMemcpyAsync(extracted, c->fe_extracted.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+    if (col_ind) RG_CUDA(c, cudaMemcpyAsync(col_ind, c->fe_col.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (point_range) RG_CUDA(c, cudaMemcpyAsync(point_range, c->fe_prange.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  }
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RG_OK;
+}
+
+int rg_feature_extraction(rg_ctx* c, const float* extracted, const int32_t* col_ind, const float* point_range, const int32_t* start_ring,
+                          const int32_t* end_ring, int32_t n, const rg_feature_params* p, float* curvature, int32_t* picked, int32_t* label,
+                          float* corner, int32_t* n_corner, float* surface, int32_t* n_surface) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (!p || !extracted || !col_ind || !point_range || !start_ring || !end_ring || !n_corner || !n_surface)
+    return set_err(c, RG_ERR_INVALID, "rg_feature_extraction: null argument");
+  if (p->n_scan < 1 || p->horizon_scan < 1 || n < 1 || (size_t)n > (size_t)p->n_scan * p->horizon_scan || !(p->surf_leaf_size > 0.f))
+    return set_err(c, RG_ERR_INVALID, "rg_feature_extraction: bad parameters");
+  if (p->horizon_scan > FE_RING_CAP) return set_err(c, RG_ERR_UNSUPPORTED, "rg_feature_extraction: horizon_scan above the per-ring capacity (2048)");
+  if (int rc = fe_alloc(c, p->n_scan, p->horizon_scan)) return rc;
+  RG_CUDA(c, cudaMemcpyAsync(c->fe_extracted.p, extracted, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  RG_CUDA(c, cudaMemcpyAsync(c->fe_col.p, col_ind, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  RG_CUDA(c, cudaMemcpyAsync(c->fe_prange.p, point_range, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  RG_CUDA(c, cudaMemcpyAsync(c->fe_start.p, start_ring, p->n_scan * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  RG_CUDA(c, cudaMemcpyAsync(c->fe_end.p, end_ring, p->n_scan * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  RG_CUDA(c, cudaMemsetAsync(c->fe_counts.p, 0, 8 * sizeof(int), c->stream));
+  FeatLaunch L;
+  L.extracted = c->fe_extracted.p; L.col_ind = c->fe_col.p; L.point_range = c->fe_prange.p; L.start_ring = c->fe_start.p; L.end_ring = c->fe_end.p;
+  L.n_dev = nullptr; L.n = n; L.n_scan = p->n_scan; L.horizon = p->horizon_scan;
+  L.edge_thr = p->edge_threshold; L.surf_thr = p->surf_threshold; L.leaf = p->surf_leaf_size;
+  L.curvature = c->fe_curv.p; L.picked = c->fe_picked.p; L.label = c->fe_label.p;
+  L.corner_ring = c->fe_corner_ring.p; L.corner_cnt = c->fe_corner_cnt.p; L.surf_ring = c->fe_surf_ring.p; L.surf_cnt = c->fe_surf_cnt.p;
+  L.corner_out = c->fe_corner_out.p; L.n_corner = c->fe_counts.p + 1; L.surf_out = c->fe_surf_out.p; L.n_surf = c->fe_counts.p + 2;
+  L.error_flag = c->fe_counts.p + 3;
+  RG_CUDA(c, launch_features(L, c->stream));
+  g_launches += 5;
+  int h[4] = {0, 0, 0, 0};
+  RG_CUDA(c, cudaMemcpyAsync(h, c->fe_counts.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (h[3] != 0) return set_err(c, RG_ERR_UNSUPPORTED, "rg_feature_extraction: sector/ring capacity exceeded or inconsistent ring indices");
+  *n_corner = h[1]; *n_surface = h[2];
+  if (curvature) RG_CUDA(c, cudaMemcpyAsync(curvature, c->fe_curv.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (picked) RG_CUDA(c, cudaMemcpyAsync(picked, c->fe_picked.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (label) RG_CUDA(c, cudaMemcpyAsync(label, c->fe_label.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (corner && h[1] > 0) RG_CUDA(c, cudaMemcpyAsync(corner, c->fe_corner_out.p, (size_t)h[1] * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  if (surface && h[2] > 0) RG_CUDA(c, cudaMemcpyAsync(surface, c->fe_surf_out.p, (size_t)h[2] * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RG_OK;
 }
 
 }  // extern "C"

@@ -200,3 +200,27 @@ def scan_torch(scene: dict, T_ws: np.ndarray, sensor: str = "os1-128", sigma: fl
     pts = torch.ones((d_s.shape[0], 4), dtype=torch.float32, device=device)
     pts[:, :3] = (d_s * t[:, None]).to(torch.float32)
     return pts
+
+
+def raw_frame(scene: dict, T_ws: np.ndarray, sensor: str = "os1-128", sigma: float = 0.02, seed: int = 1234, extra: int = 0) -> np.ndarray:
+    """A raw driver frame in the reference's VelodynePointXYZIRT layout (imageProjection.cpp:7-19), points in firing
+    order (all rings of azimuth step 0, then step 1, ...). `extra` appends jittered duplicates of random points so that
+    several points compete for one range-image cell (exercises "first point wins", imageProjection.cpp:451)."""
+    from .frontend import RAW_POINT_DTYPE
+    pts, ring, col = scan(scene, T_ws, sensor, sigma, seed, return_meta=True)
+    rings, cols, _, _ = SENSORS[sensor]
+    order = np.lexsort((ring, col))
+    pts, ring, col = pts[order], ring[order], col[order]
+    if extra:
+        rng = np.random.default_rng(seed + 1)
+        pick = rng.integers(0, pts.shape[0], size=extra)
+        dup = pts[pick].copy()
+        dup[:, :3] *= (1.0 + rng.normal(0.0, 2e-3, size=(extra, 1))).astype(np.float32)
+        where = np.sort(rng.integers(0, pts.shape[0], size=extra))
+        pts = np.insert(pts, where, dup, axis=0); ring = np.insert(ring, where, ring[pick]); col = np.insert(col, where, col[pick])
+    raw = np.zeros(pts.shape[0], dtype=RAW_POINT_DTYPE)
+    raw["x"], raw["y"], raw["z"] = pts[:, 0], pts[:, 1], pts[:, 2]
+    raw["intensity"] = 1.0
+    raw["ring"] = ring.astype(np.uint16)
+    raw["time"] = (col.astype(np.float32) / cols) * 0.1
+    return raw
