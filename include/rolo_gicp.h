@@ -170,6 +170,10 @@ unsigned long long rg_kernel_launch_count(void);
  * registration. on_device != 0: buf is a device pointer (NCCL path); else host pointer (gloo / tests).   */
 typedef int (*rg_reduce_fn)(void* user, double* buf, int count, int on_device, void* stream);
 int rg_set_reduce_hook(rg_ctx*, rg_reduce_fn fn, void* user, int on_device);
+/* Restrict every evaluation (linearize / compute_error / t3) to source points [lo, hi) while covariances stay those of
+ * the FULL cloud (kNN neighbourhoods must not be cut at shard borders). lo must be a multiple of 256 (the TMA tile);
+ * lo == hi == 0 restores the whole cloud. Reset by rg_set_input_source*. */
+int rg_set_source_shard(rg_ctx*, size_t lo, size_t hi);
 
 /* ---- upstream range-image passes ------------------------------------------------------------------------ */
 /* ImageProjection::projectPointCloud + cloudExtraction (imageProjection.cpp:399-505), deskew disabled

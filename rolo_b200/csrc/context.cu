@@ -250,6 +250,7 @@ struct rg_ctx {
   double last_kernel_us = -1.0;
 
   rg_reduce_fn reduce_fn = nullptr; void* reduce_user = nullptr; int reduce_on_device = 0;
+  int shard_lo = 0, shard_hi = 0;       // evaluation range within the source cloud (0,0 = all)
 
   // front end (range-image projection + feature extraction) scratch
   DevBuf<unsigned char> fe_raw;
@@ -454,8 +455,10 @@ int prepare_linearize(rg_ctx* c) {
   const int noff = noff_of(c->search_method);
   if (c->st_ok && c->corr_noff == noff) return RG_OK;
   const int n_pairs = c->batch ? (int)c->batch->pairs.size() : 1;
-  c->blocks_per_pair = choose_blocks_per_pair(c->device, c->src.n, n_pairs);
-  RG_CUDA(c, c->corr.ensure(c->device, (size_t)c->src.n * noff));
+  const int lo = (c->shard_hi > c->shard_lo) ? c->shard_lo : 0;
+  const int n_eval = (c->shard_hi > c->shard_lo) ? (c->shard_hi - c->shard_lo) : c->src.n;
+  c->blocks_per_pair = choose_blocks_per_pair(c->device, n_eval, n_pairs);
+  RG_CUDA(c, c->corr.ensure(c->device, (size_t)n_eval * noff));
   c->corr_noff = noff; c->have_corr = false;
   RG_CUDA(c, c->partials.ensure(c->device, (size_t)c->blocks_per_pair * RES_N));
   if (!c->counter.p) { RG_CUDA(c, c->counter.ensure(c->device, 4)); RG_CUDA(c, cudaMemsetAsync(c->counter.p, 0, 4 * sizeof(unsigned), c->stream)); }
@@ -471,7 +474,7 @@ int prepare_linearize(rg_ctx* c) {
     }
   }
   LinStatic st;
-  st.src = c->src.pts.p; st.cov6 = c->src.cov6.p; st.n = c->src.n; st.mask = c->mask; st.table = c->table.p; st.vox = c->vox.p;
+  st.src = c->src.pts.p + lo; st.cov6 = c->src.cov6.p + (size_t)(lo / TILE_PTS) * COV_PLANES * TILE_PTS; st.n = n_eval; st.mask = c->mask; st.table = c->table.p; st.vox = c->vox.p;
   st.corr = c->corr.p; st.partials = c->partials.p; st.counter = c->counter.p;
   const bool to_host = !c->batch && !(c->reduce_fn && c->reduce_on_device);
   if (c->batch) { c->result_view = c->batch->result_host + (size_t)c->batch_index * RES_N; c->flag_view = c->batch->flag_host + c->batch_index; }
@@ -699,7 +702,7 @@ double rg_last_kernel_us(const rg_ctx* c) { return c ? c->last_kernel_us : -1.0;
 int rg_set_input_source(rg_ctx* c, const float* pts, size_t n, size_t stride) {
   CHECK_CTX(c);
   int rc = upload_cloud(c, c->src, pts, n, stride);
-  c->st_ok = false; c->have_corr = false;
+  c->st_ok = false; c->have_corr = false; c->shard_lo = c->shard_hi = 0;
   return rc;
 }
 int rg_set_input_target(rg_ctx* c, const float* pts, size_t n, size_t stride) {
@@ -711,7 +714,7 @@ int rg_set_input_target(rg_ctx* c, const float* pts, size_t n, size_t stride) {
 int rg_set_input_source_device(rg_ctx* c, const float* dev, size_t n, void* stream) {
   CHECK_CTX(c);
   int rc = upload_cloud_device(c, c->src, dev, n, (cudaStream_t)stream);
-  c->st_ok = false; c->have_corr = false;
+  c->st_ok = false; c->have_corr = false; c->shard_lo = c->shard_hi = 0;
   return rc;
 }
 int rg_set_input_target_device(rg_ctx* c, const float* dev, size_t n, void* stream) {
@@ -903,7 +906,7 @@ int rg_get_correspondence_keys(rg_ctx* c, int32_t* keys) {
   if (!c->have_corr) return set_err(c, RG_ERR_INVALID, "no correspondences yet");
   const int V = fetch_voxel_count(c);
   if (V < 0) return RG_ERR_INVALID;
-  const size_t m = (size_t)c->src.n * c->corr_noff;
+  const size_t m = (size_t)((c->shard_hi > c->shard_lo) ? (c->shard_hi - c->shard_lo) : c->src.n) * c->corr_noff;
   std::vector<int> hc(m);
   RG_CUDA(c, cudaMemcpyAsync(hc.data(), c->corr.p, sizeof(int) * m, cudaMemcpyDeviceToHost, c->stream));
   std::vector<VoxSlot> ht((size_t)c->mask + 1);
@@ -940,6 +943,14 @@ int rg_knn(rg_ctx* c, int which, int k, int32_t* out) {
   RG_CUDA(c, cudaMemcpyAsync(out, dk.p, sizeof(int) * (size_t)n * k, cudaMemcpyDeviceToHost, c->stream));
   RG_CUDA(c, cudaStreamSynchronize(c->stream));
   dk.release();
+  return RG_OK;
+}
+
+int rg_set_source_shard(rg_ctx* c, size_t lo, size_t hi) {
+  CHECK_CTX(c);
+  if (lo == 0 && hi == 0) { c->shard_lo = c->shard_hi = 0; c->st_ok = false; c->have_corr = false; return RG_OK; }
+  if (lo % TILE_PTS != 0 || hi <= lo || hi > (size_t)c->src.n) return set_err(c, RG_ERR_INVALID, "rg_set_source_shard: need lo % 256 == 0 and lo < hi <= source size");
+  c->shard_lo = (int)lo; c->shard_hi = (int)hi; c->st_ok = false; c->have_corr = false;
   return RG_OK;
 }
 

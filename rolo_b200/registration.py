@@ -230,6 +230,8 @@ class RotVGICP:
     def lastKernelUs(self): return self._L.rg_last_kernel_us(self._h)
     def stream(self): return self._L.rg_stream(self._h)
 
+    def setSourceShard(self, lo: int, hi: int): self._ck(self._L.rg_set_source_shard(self._h, lo, hi))
+
     def setReduceHook(self, fn, on_device: bool):
         """Sharded registration (config 4): fn(buf_ptr:int, count:int, on_device:bool, stream:int) -> int."""
         if fn is None:
