@@ -288,7 +288,8 @@ def main():
     traffic = ncu_traffic()
     roofline = {"bound": "hbm", "kernel": "rolo::linearize_kernel<SE3,refresh,DIRECT1> (fused correspondence+Mahalanobis+Jacobian+reduction)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                "traffic": (traffic["dram_bytes_per_point"] * N_POINTS * P) if traffic else None,
+                "traffic_source": traffic["capture"] if traffic else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
                 "launch_us": lin_us, "launches_timed": lin_n, "points_per_launch": N_POINTS * P}
 
