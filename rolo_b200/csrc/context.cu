@@ -227,7 +227,7 @@ struct rg_ctx {
   DevBuf<int> idx_in, idx_out, bbox;
   DevBuf<float4> sorted;
   DevBuf<unsigned char> cub_temp;
-  DevBuf<int> knn_idx;
+  DevBuf<int> knn_idx, bucket_start;
 
   // linearize
   DevBuf<int> corr; int corr_noff = 0;
@@ -361,7 +361,7 @@ int calc_cov(rg_ctx* c, Cloud& cl) {
   const int n = cl.n;
   RG_CUDA(c, c->codes_in.ensure(c->device, n)); RG_CUDA(c, c->codes_out.ensure(c->device, n));
   RG_CUDA(c, c->idx_in.ensure(c->device, n)); RG_CUDA(c, c->idx_out.ensure(c->device, n));
-  RG_CUDA(c, c->sorted.ensure(c->device, n)); RG_CUDA(c, c->bbox.ensure(c->device, 8));
+  RG_CUDA(c, c->sorted.ensure(c->device, n)); RG_CUDA(c, c->bbox.ensure(c->device, 8)); RG_CUDA(c, c->bucket_start.ensure(c->device, cov_bucket_table_entries()));
   const size_t tb = cov_cub_temp_bytes(n);
   RG_CUDA(c, c->cub_temp.ensure(c->device, tb));
   RG_CUDA(c, c->knn_idx.ensure(c->device, (size_t)n * c->k_correspondences));
@@ -369,11 +369,11 @@ int calc_cov(rg_ctx* c, Cloud& cl) {
   L.pts = cl.pts.p; L.n = n; L.k = c->k_correspondences; L.method = c->regularization_method;
   L.cov6 = cl.cov6.p; L.knn = c->knn_idx.p;
   L.s.codes_in = c->codes_in.p; L.s.codes_out = c->codes_out.p; L.s.idx_in = c->idx_in.p; L.s.idx_out = c->idx_out.p;
-  L.s.sorted = c->sorted.p; L.s.cub_temp = c->cub_temp.p; L.s.cub_temp_bytes = tb; L.s.bbox = c->bbox.p;
+  L.s.sorted = c->sorted.p; L.s.cub_temp = c->cub_temp.p; L.s.cub_temp_bytes = tb; L.s.bbox = c->bbox.p; L.s.bucket_start = c->bucket_start.p;
   // zero the padding rows of the covariance tiles (only the last tile has any)
   if (cl.n_pad > n) RG_CUDA(c, cudaMemsetAsync(cl.cov6.p + (size_t)(cl.n_pad / TILE_PTS - 1) * COV_PLANES * TILE_PTS, 0, sizeof(float) * COV_PLANES * TILE_PTS, c->stream));
   RG_CUDA(c, launch_covariances(L, c->stream));
-  g_launches += 6;   // bbox_init, bbox, morton, gather, knn, cov (cub's radix-sort kernels not counted)
+  g_launches += 7;   // bbox_init, bbox, morton, gather, bucket table, knn, cov (cub's radix-sort kernels not counted)
   cl.has_cov = true;
   return RG_OK;
 }
@@ -656,7 +656,7 @@ void rg_destroy(rg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->src.release(); c->tgt.release();
   c->table.release(); c->vox.release(); c->sums.release(); c->slot_of_point.release(); c->counters.release();
-  c->codes_in.release(); c->codes_out.release(); c->idx_in.release(); c->idx_out.release(); c->bbox.release(); c->sorted.release(); c->cub_temp.release(); c->knn_idx.release();
+  c->codes_in.release(); c->codes_out.release(); c->idx_in.release(); c->idx_out.release(); c->bbox.release(); c->sorted.release(); c->cub_temp.release(); c->knn_idx.release(); c->bucket_start.release();
   c->fe_raw.release(); c->fe_owner.release(); c->fe_row_count.release(); c->fe_col.release(); c->fe_start.release(); c->fe_end.release();
   c->fe_counts.release(); c->fe_picked.release(); c->fe_label.release(); c->fe_corner_cnt.release(); c->fe_surf_cnt.release();
   c->fe_range_image.release(); c->fe_prange.release(); c->fe_curv.release(); c->fe_full.release(); c->fe_extracted.release();
@@ -930,7 +930,7 @@ int rg_knn(rg_ctx* c, int which, int k, int32_t* out) {
   if (n == 0 || k < 1 || k > 64 || n < k || !out) return set_err(c, RG_ERR_INVALID, "rg_knn: bad arguments");
   RG_CUDA(c, c->codes_in.ensure(c->device, n)); RG_CUDA(c, c->codes_out.ensure(c->device, n));
   RG_CUDA(c, c->idx_in.ensure(c->device, n)); RG_CUDA(c, c->idx_out.ensure(c->device, n));
-  RG_CUDA(c, c->sorted.ensure(c->device, n)); RG_CUDA(c, c->bbox.ensure(c->device, 8));
+  RG_CUDA(c, c->sorted.ensure(c->device, n)); RG_CUDA(c, c->bbox.ensure(c->device, 8)); RG_CUDA(c, c->bucket_start.ensure(c->device, cov_bucket_table_entries()));
   const size_t tb = cov_cub_temp_bytes(n);
   RG_CUDA(c, c->cub_temp.ensure(c->device, tb));
   DevBuf<int> dk;
@@ -938,7 +938,7 @@ int rg_knn(rg_ctx* c, int which, int k, int32_t* out) {
   CovLaunch L;
   L.pts = cl.pts.p; L.n = n; L.k = k; L.method = c->regularization_method; L.cov6 = nullptr; L.knn = dk.p;
   L.s.codes_in = c->codes_in.p; L.s.codes_out = c->codes_out.p; L.s.idx_in = c->idx_in.p; L.s.idx_out = c->idx_out.p;
-  L.s.sorted = c->sorted.p; L.s.cub_temp = c->cub_temp.p; L.s.cub_temp_bytes = tb; L.s.bbox = c->bbox.p;
+  L.s.sorted = c->sorted.p; L.s.cub_temp = c->cub_temp.p; L.s.cub_temp_bytes = tb; L.s.bbox = c->bbox.p; L.s.bucket_start = c->bucket_start.p;
   RG_CUDA(c, launch_covariances(L, c->stream));
   RG_CUDA(c, cudaMemcpyAsync(out, dk.p, sizeof(int) * (size_t)n * k, cudaMemcpyDeviceToHost, c->stream));
   RG_CUDA(c, cudaStreamSynchronize(c->stream));

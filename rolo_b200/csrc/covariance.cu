@@ -251,21 +251,60 @@ __device__ void regularize(const double cov[6], int method, double out[6]) {
 // ---------------------------------------------------------------------------------------------------
 constexpr int KNN_QPW = 4;            // queries handled sequentially by one warp
 constexpr int KNN_CAND_CAP = 1024;    // prefer a finer level when the block holds more candidates than this
+constexpr int BUCKET_BITS = 18;       // top Morton bits indexed by the bucket table (octree level 6)
+constexpr int BUCKET_SHIFT = 3 * MORTON_BITS - BUCKET_BITS;
+constexpr int N_BUCKETS = 1 << BUCKET_BITS;
 
-__device__ __forceinline__ void bitonic_cmpx(float& d, int& id, int j2, bool take_min) {
-  const float od = __shfl_xor_sync(0xffffffffu, d, j2);
-  const int oi = __shfl_xor_sync(0xffffffffu, id, j2);
-  const bool other_less = cand_less(od, oi, d, id);
-  if (take_min == other_less) { d = od; id = oi; }
+// bucket_start[b] = first sorted position whose code has top bits >= b (b = 0 .. N_BUCKETS): every later
+// lower_bound only searches inside one bucket
+__global__ void bucket_table_kernel(const unsigned long long* __restrict__ codes, int n, int* __restrict__ bucket_start) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > N_BUCKETS) return;
+  bucket_start[b] = (b == N_BUCKETS) ? n : lower_bound_u64(codes, n, (unsigned long long)b << BUCKET_SHIFT);
 }
 
+__device__ __forceinline__ int lower_bound_bucketed(const unsigned long long* __restrict__ codes, const int* __restrict__ bucket_start,
+                                                    unsigned long long key) {
+  const unsigned long long top = key >> BUCKET_SHIFT;
+  if (top >= (unsigned long long)N_BUCKETS) return __ldg(bucket_start + N_BUCKETS);
+  int lo = __ldg(bucket_start + top);
+  if ((key & ((1ull << BUCKET_SHIFT) - 1ull)) == 0ull) return lo;     // bucket-aligned key (levels <= 6)
+  int hi = __ldg(bucket_start + top + 1);
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(codes + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ unsigned compact21(unsigned long long x) {   // inverse of expand21
+  x &= 0x1249249249249249ull;
+  x = (x ^ (x >> 2)) & 0x10C30C30C30C30C3ull;
+  x = (x ^ (x >> 4)) & 0x100F00F00F00F00Full;
+  x = (x ^ (x >> 8)) & 0x1F0000FF0000FFull;
+  x = (x ^ (x >> 16)) & 0x1F00000000FFFFull;
+  x = (x ^ (x >> 32)) & 0x1FFFFFull;
+  return (unsigned)x;
+}
+
+// candidates are ordered by the packed key (float distance bits << 32 | index): distances are >= +0, so the
+// unsigned bit pattern is monotone, and the index breaks ties exactly like the oracle's (distance, index) order
+__device__ __forceinline__ void bitonic_cmpx(unsigned long long& key, int j2, bool take_min) {
+  const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j2);
+  if (take_min == (other < key)) key = other;
+}
+constexpr unsigned long long KEY_INF = 0x7F7FFFFF7FFFFFFFull;            // (FLT_MAX, INT_MAX)
+
 __global__ void __launch_bounds__(256)
-knn_warp_kernel(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes, int n, int k,
-                const int* __restrict__ bbox, int* __restrict__ knn_out) {
+knn_warp_kernel(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes, const int* __restrict__ bucket_start,
+                int n, int k, const int* __restrict__ bbox, int* __restrict__ knn_out) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const Quant qn = make_quant(bbox);
+
+  // ranges of the previous query of this warp: consecutive Morton neighbours usually share the block
+  int prevL = -1, prev_cx = 0, prev_cy = 0, prev_cz = 0, lo = 0, cnt = 0, incl = 0, total = 0;
 
   #pragma unroll 1
   for (int qq = 0; qq < KNN_QPW; qq++) {
@@ -273,48 +312,55 @@ knn_warp_kernel(const float4* __restrict__ sorted, const unsigned long long* __r
     if (j >= n) break;                                   // warp-uniform
     const float4 q = __ldg(sorted + j);
     const int self = __float_as_int(q.w);
-    unsigned ix, iy, iz;
-    quantize(qn, q.x, q.y, q.z, ix, iy, iz);
-    const double rel[3] = {(double)q.x - qn.mn[0], (double)q.y - qn.mn[1], (double)q.z - qn.mn[2]};
+    const unsigned long long cq = __ldg(codes + j);
+    const unsigned ix = compact21(cq), iy = compact21(cq >> 1), iz = compact21(cq >> 2);
 
-    // start level: the level-cpl(code[j], code[j-4]) cell holds the sorted entries j-4..j (likewise on the
-    // right): the larger of the two common prefixes is a boundary-robust first guess
+    // start level: reuse the previous query's final level when this query lies in the same cell there; otherwise
+    // the level-cpl(code[j], code[j-4]) cell holds the sorted entries j-4..j (likewise on the right), so the
+    // larger of the two common prefixes is a boundary-robust first guess
     int L;
-    {
-      const unsigned long long cq = __ldg(codes + j);
+    bool reuse = false;
+    if (prevL >= 0 && (int)(ix >> (MORTON_BITS - prevL)) == prev_cx && (int)(iy >> (MORTON_BITS - prevL)) == prev_cy &&
+        (int)(iz >> (MORTON_BITS - prevL)) == prev_cz) {
+      L = prevL; reuse = true;
+    } else {
       const unsigned long long xl = cq ^ __ldg(codes + max(j - 4, 0)), xr = cq ^ __ldg(codes + min(j + 4, n - 1));
       const int bl = (j - 4 >= 0) ? (xl ? (__clzll((long long)xl) - 1) : 63) : 0;     // codes use 63 bits
       const int br = (j + 4 < n) ? (xr ? (__clzll((long long)xr) - 1) : 63) : 0;
       L = min(max(bl, br) / 3, MORTON_BITS);
     }
 
-    float td = FLT_MAX; int tid = INT_MAX;               // this lane's element of the sorted top-32
-    bool no_finer = false;
+    unsigned long long top = KEY_INF;                   // this lane's element of the sorted top-32
+    bool no_finer = reuse;
     #pragma unroll 1
     for (;;) {
       const int sh = MORTON_BITS - L;
       const int cx = (int)(ix >> sh), cy = (int)(iy >> sh), cz = (int)(iz >> sh);
       const int ncell = 1 << L;
-      int lo = 0, cnt = 0;
-      if (lane < 27) {
-        const int oo = (lane == 0) ? 13 : (lane <= 13 ? lane - 1 : lane);   // centre cell first
-        const int nx = cx + oo % 3 - 1, ny = cy + (oo / 3) % 3 - 1, nz = cz + oo / 9 - 1;
-        if (nx >= 0 && ny >= 0 && nz >= 0 && nx < ncell && ny < ncell && nz < ncell) {
-          const unsigned long long pre = morton3((unsigned)nx, (unsigned)ny, (unsigned)nz);
-          lo = lower_bound_u64(codes, n, pre << (3 * sh));
-          const int hi = (L == 0) ? n : lower_bound_u64(codes, n, (pre + 1ull) << (3 * sh));
-          cnt = hi - lo;
+      if (!reuse) {
+        lo = 0; cnt = 0;
+        if (lane < 27) {
+          const int oo = (lane == 0) ? 13 : (lane <= 13 ? lane - 1 : lane);   // centre cell first
+          const int nx = cx + oo % 3 - 1, ny = cy + (oo / 3) % 3 - 1, nz = cz + oo / 9 - 1;
+          if (nx >= 0 && ny >= 0 && nz >= 0 && nx < ncell && ny < ncell && nz < ncell) {
+            const unsigned long long pre = morton3((unsigned)nx, (unsigned)ny, (unsigned)nz);
+            lo = lower_bound_bucketed(codes, bucket_start, pre << (3 * sh));
+            const int hi = (L == 0) ? n : lower_bound_bucketed(codes, bucket_start, (pre + 1ull) << (3 * sh));
+            cnt = hi - lo;
+          }
         }
+        incl = cnt;
+        #pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
+        total = __shfl_sync(FULL, incl, 31);
+        if (!no_finer && total > KNN_CAND_CAP && L < MORTON_BITS) { L++; continue; }
+        if (total < k && L > 0) { no_finer = true; L--; continue; }
       }
-      int incl = cnt;
-      #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
-      const int total = __shfl_sync(FULL, incl, 31);
-      if (!no_finer && total > KNN_CAND_CAP && L < MORTON_BITS) { L++; continue; }
-      if (total < k && L > 0) { no_finer = true; L--; continue; }
+      reuse = false;
+      prevL = L; prev_cx = cx; prev_cy = cy; prev_cz = cz;
       const int excl = incl - cnt;
 
-      td = FLT_MAX; tid = INT_MAX;
+      top = KEY_INF;
       #pragma unroll 1
       for (int base = 0; base < total; base += 32) {
         const int g = base + lane;
@@ -329,49 +375,46 @@ knn_warp_kernel(const float4* __restrict__ sorted, const unsigned long long* __r
         }
         a = min(a, 26);
         const int cell_lo = __shfl_sync(FULL, lo, a), cell_ex = __shfl_sync(FULL, excl, a);
-        float d = FLT_MAX; int pid = INT_MAX;
+        unsigned long long key = KEY_INF;
         if (valid) {
           const float4 p = __ldg(sorted + cell_lo + (g - cell_ex));
           const float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
-          d = __fmul_rn(dx, dx);
+          float d = __fmul_rn(dx, dx);
           d = __fadd_rn(d, __fmul_rn(dy, dy));
           d = __fadd_rn(d, __fmul_rn(dz, dz));
-          pid = __float_as_int(p.w);
+          key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
         }
-        const float kd = __shfl_sync(FULL, td, k - 1);
-        const int kid = __shfl_sync(FULL, tid, k - 1);
-        const bool pass = valid && cand_less(d, pid, kd, kid);
+        const unsigned long long kth = __shfl_sync(FULL, top, k - 1);
+        const bool pass = key < kth;
         unsigned m = __ballot_sync(FULL, pass);
         if (m == 0) continue;
         if (__popc(m) > 6) {
           // bitonic sort of the batch (non-passing lanes carry +inf), then bitonic merge with the top-32
-          if (!pass) { d = FLT_MAX; pid = INT_MAX; }
+          if (!pass) key = KEY_INF;
           #pragma unroll
           for (int k2 = 2; k2 <= 32; k2 <<= 1) {
             #pragma unroll
-            for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) bitonic_cmpx(d, pid, j2, ((lane & k2) == 0) == ((lane & j2) == 0));
+            for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) bitonic_cmpx(key, j2, ((lane & k2) == 0) == ((lane & j2) == 0));
           }
-          const float rd = __shfl_sync(FULL, d, 31 - lane);
-          const int ri = __shfl_sync(FULL, pid, 31 - lane);
-          if (cand_less(rd, ri, td, tid)) { td = rd; tid = ri; }
+          const unsigned long long rev = __shfl_sync(FULL, key, 31 - lane);
+          if (rev < top) top = rev;
           #pragma unroll
-          for (int j2 = 16; j2 > 0; j2 >>= 1) bitonic_cmpx(td, tid, j2, (lane & j2) == 0);
+          for (int j2 = 16; j2 > 0; j2 >>= 1) bitonic_cmpx(top, j2, (lane & j2) == 0);
         } else {
           while (m) {
             const int srcl = __ffs(m) - 1;
             m &= m - 1;
-            const float cd = __shfl_sync(FULL, d, srcl);
-            const int ci = __shfl_sync(FULL, pid, srcl);
-            const int pos = __popc(__ballot_sync(FULL, cand_less(td, tid, cd, ci)));   // elements that stay in front
-            const float ud = __shfl_up_sync(FULL, td, 1);
-            const int ui = __shfl_up_sync(FULL, tid, 1);
-            if (lane > pos) { td = ud; tid = ui; } else if (lane == pos) { td = cd; tid = ci; }
+            const unsigned long long ck = __shfl_sync(FULL, key, srcl);
+            const int pos = __popc(__ballot_sync(FULL, top < ck));      // elements that stay in front
+            const unsigned long long up = __shfl_up_sync(FULL, top, 1);
+            if (lane > pos) top = up; else if (lane == pos) top = ck;
           }
         }
       }
       if (L == 0) break;
       // exact iff the k-th neighbour lies inside the guaranteed-complete radius of the scanned block
       const double sL = qn.cell * (double)(1 << sh);
+      const double rel[3] = {(double)q.x - qn.mn[0], (double)q.y - qn.mn[1], (double)q.z - qn.mn[2]};
       double rs = 1e300;
       const int cc[3] = {cx, cy, cz};
       #pragma unroll
@@ -379,13 +422,12 @@ knn_warp_kernel(const float4* __restrict__ sorted, const unsigned long long* __r
         if (cc[dd] - 1 >= 0) rs = fmin(rs, rel[dd] - (double)(cc[dd] - 1) * sL);
         if (cc[dd] + 1 < ncell) rs = fmin(rs, (double)(cc[dd] + 2) * sL - rel[dd]);
       }
-      const float kd = __shfl_sync(FULL, td, k - 1);
-      const int kid = __shfl_sync(FULL, tid, k - 1);
-      if (kid != INT_MAX && (double)kd <= rs * rs * (1.0 - 1e-6)) break;
+      const unsigned long long kth = __shfl_sync(FULL, top, k - 1);
+      if (kth != KEY_INF && (double)__uint_as_float((unsigned)(kth >> 32)) <= rs * rs * (1.0 - 1e-6)) break;
       no_finer = true;
       L--;
     }
-    if (lane < k) knn_out[(size_t)self * k + lane] = tid;
+    if (lane < k) knn_out[(size_t)self * k + lane] = (int)(unsigned)(top & 0xFFFFFFFFull);
   }
 }
 
@@ -474,6 +516,8 @@ cov_from_knn_kernel(const float4* __restrict__ pts, const int* __restrict__ knn,
 
 }  // namespace
 
+size_t cov_bucket_table_entries() { return (size_t)N_BUCKETS + 1; }
+
 size_t cov_cub_temp_bytes(int n) {
   size_t bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
@@ -496,7 +540,8 @@ cudaError_t launch_covariances(const CovLaunch& L, cudaStream_t stream) {
   gather_sorted_kernel<<<nb, tb, 0, stream>>>(L.pts, L.s.idx_out, n, L.s.sorted);
   if (L.k <= 32) {
     const int queries_per_block = (256 / 32) * KNN_QPW;
-    knn_warp_kernel<<<(n + queries_per_block - 1) / queries_per_block, 256, 0, stream>>>(L.s.sorted, L.s.codes_out, n, L.k, L.s.bbox, L.knn);
+    bucket_table_kernel<<<(N_BUCKETS + 1 + tb - 1) / tb, tb, 0, stream>>>(L.s.codes_out, n, L.s.bucket_start);
+    knn_warp_kernel<<<(n + queries_per_block - 1) / queries_per_block, 256, 0, stream>>>(L.s.sorted, L.s.codes_out, L.s.bucket_start, n, L.k, L.s.bbox, L.knn);
   } else {
     knn_thread_kernel<<<(n + 127) / 128, 128, 0, stream>>>(L.s.sorted, L.s.codes_out, n, L.k, L.s.bbox, L.knn);
   }

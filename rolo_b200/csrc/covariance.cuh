@@ -13,9 +13,11 @@ struct CovScratch {           // all device pointers; sized for n points (see co
   void* cub_temp;
   size_t cub_temp_bytes;
   int* bbox;                      // [6] ordered-int min xyz / max xyz
+  int* bucket_start;              // [cov_bucket_table_entries()] first sorted position per top-18-bit Morton bucket
 };
 
 size_t cov_cub_temp_bytes(int n);
+size_t cov_bucket_table_entries();
 
 struct CovLaunch {
   const float4* pts;          // [n] (w ignored)

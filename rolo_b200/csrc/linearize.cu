@@ -25,6 +25,9 @@ namespace {
 
 constexpr int NTHREADS = TILE_PTS;               // 256
 constexpr int NWARPS = NTHREADS / 32;
+#ifndef LIN_MINBLOCKS
+#define LIN_MINBLOCKS 2
+#endif
 constexpr int NSTAGES = 4;                       // TMA ring depth (4 x 10 KB per CTA)
 constexpr uint32_t PTS_TILE_BYTES = TILE_PTS * sizeof(float4);             // 4096
 constexpr uint32_t COV_TILE_BYTES = TILE_PTS * COV_PLANES * sizeof(float); // 6144
@@ -77,7 +80,7 @@ template <int MODE> struct AccN { static constexpr int value = (MODE == LIN_SE3)
 // COST: [0] cost, [1] count
 
 template <int MODE, bool REFRESH, int NOFF>
-__global__ void __launch_bounds__(NTHREADS, 2)
+__global__ void __launch_bounds__(NTHREADS, LIN_MINBLOCKS)
 linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict__ dyn_arr, const __grid_constant__ LinDyn dyn0, int blocks_per_pair) {
   constexpr int NACC = AccN<MODE>::value;
   __shared__ __align__(128) float4 s_pts[NSTAGES][TILE_PTS];
