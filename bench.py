@@ -113,6 +113,21 @@ def offsets_for(rank: int, pairs: int):
     return [synth.random_offset(rng) for _ in range(pairs)]
 
 
+def pick_threads(o, pair):
+    """All host threads the CPU arm can use: os.cpu_count() (torchrun exports OMP_NUM_THREADS=1, so the OpenMP default
+    is not trusted); if half as many threads (physical cores on an SMT host) is faster on one registration, use that."""
+    full = os.cpu_count() or 1
+    best, best_dt = full, None
+    for nt in sorted({full, max(1, full // 2)}, reverse=True):
+        o.setNumThreads(nt)
+        o.setInputTarget(pair[0]); o.setInputSource(pair[1])
+        t0 = time.perf_counter(); o.align(); dt = time.perf_counter() - t0
+        if best_dt is None or dt < best_dt:
+            best, best_dt = nt, dt
+    o.setNumThreads(best)
+    return best
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of the reference algorithm, all host threads, same workload per registration."""
     if rank != 0:
@@ -123,10 +138,9 @@ def run_reference(args, rank, world):
     Ts = offsets_for(0, 2)
     clouds = [(synth.scan(scene, np.eye(4), SENSOR, seed=1234 + i), synth.scan(scene, Ts[i], SENSOR, seed=5678 + i)) for i in range(2)]
     o = ob.Oracle()
-    o.setNumThreads(0)
-    cores = o.getNumThreads()
     o.setPolarResolution(*POLAR); o.setOptimizerType(ob.OPT_GAUSS_NEWTON); o.setMaximumIterations(GN_ITERS)
     o.setRotationEpsilon(1e-30); o.setTransformationEpsilon(1e-30)
+    cores = pick_threads(o, clouds[0])
 
     def step(i):
         t, s = clouds[i % 2]
@@ -159,10 +173,9 @@ def cpu_baseline_sample(clouds_host):
     """Bounded CPU sample on rank 0: a few full registrations with the oracle port (reported, not a target)."""
     from oracle import binding as ob
     o = ob.Oracle()
-    o.setNumThreads(0)
-    cores = o.getNumThreads()
     o.setPolarResolution(*POLAR); o.setOptimizerType(ob.OPT_GAUSS_NEWTON); o.setMaximumIterations(GN_ITERS)
     o.setRotationEpsilon(1e-30); o.setTransformationEpsilon(1e-30)
+    cores = pick_threads(o, clouds_host[0])
     n = 0
     t0 = time.perf_counter()
     poses = []

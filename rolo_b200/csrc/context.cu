@@ -273,6 +273,9 @@ struct rg_batch {
   unsigned* flag_host = nullptr;        // mapped pinned [P]
   std::vector<int> active;
   DevBuf<LinStatic> st_sub; DevBuf<LinDyn> dyn_sub;
+  std::vector<cudaStream_t> setup_streams;   // covariance / voxel-map stages of different pairs overlap on these
+  std::vector<cudaEvent_t> setup_events;
+  cudaEvent_t ev_inputs = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double lin_us_sum = 0; int lin_launches = 0;
   std::string err;
@@ -988,6 +991,15 @@ int rg_batch_create(int device, int n_pairs, rg_batch** out) {
   if (!ok) { rg_batch_destroy(b); return set_err(nullptr, RG_ERR_CUDA, "rg_batch_create: allocation failed"); }
   std::memset(b->flag_host, 0, sizeof(unsigned) * n_pairs);
   cudaEventCreate(&b->ev0); cudaEventCreate(&b->ev1);
+  cudaEventCreateWithFlags(&b->ev_inputs, cudaEventDisableTiming);
+  const int n_setup = std::min(n_pairs, 4);
+  for (int i = 0; i < n_setup; i++) {
+    cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
+    if (pool().stream_get(b->device, &st) != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+      rg_batch_destroy(b); return set_err(nullptr, RG_ERR_CUDA, "rg_batch_create: stream/event creation failed");
+    }
+    b->setup_streams.push_back(st); b->setup_events.push_back(ev);
+  }
   *out = b;
   return RG_OK;
 }
@@ -1003,6 +1015,9 @@ void rg_batch_destroy(rg_batch* b) {
   if (b->flag_host) pool().pinned_free(b->flag_host);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
+  if (b->ev_inputs) cudaEventDestroy(b->ev_inputs);
+  for (auto ev : b->setup_events) cudaEventDestroy(ev);
+  for (auto st : b->setup_streams) { cudaStreamSynchronize(st); pool().stream_put(b->device, st); }
   delete b;
 }
 
@@ -1017,16 +1032,27 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
   if (!b || !out_T) return set_err(nullptr, RG_ERR_INVALID, "rg_batch_align: bad arguments");
   const int P = (int)b->pairs.size();
   if (cudaSetDevice(b->device) != cudaSuccess) return set_err(nullptr, RG_ERR_CUDA, "cudaSetDevice failed");
-  // stage 1+2: covariances and voxel maps of every pair (stream-ordered, no host sync in between)
+  // stage 1+2: covariances and voxel maps of every pair. Pairs are spread over a few setup streams so that the
+  // small, latency-bound kernels of one pair (radix-sort passes, bbox, Morton codes, voxel insert) overlap the
+  // big kNN kernels of the others; the batch stream joins them before the lock-step iterations start.
   int noff = -1, bpp = -1;
-  for (int i = 0; i < P; i++) {
+  const int S = (int)b->setup_streams.size();
+  RG_CUDA(nullptr, cudaEventRecord(b->ev_inputs, b->stream));
+  for (int si = 0; si < S; si++) RG_CUDA(nullptr, cudaStreamWaitEvent(b->setup_streams[si], b->ev_inputs, 0));
+  int rc_setup = RG_OK;
+  for (int i = 0; i < P && rc_setup == RG_OK; i++) {
     rg_ctx* c = b->pairs[i];
-    if (c->src.n == 0 || c->tgt.n == 0) return set_err(c, RG_ERR_INVALID, "batch align: source/target cloud not set");
+    if (c->src.n == 0 || c->tgt.n == 0) { rc_setup = set_err(c, RG_ERR_INVALID, "batch align: source/target cloud not set"); break; }
     c->voxel_ok = false; c->st_ok = false; c->have_corr = false;
-    if (int rc = check_grid(c)) return rc;
-    if (int rc = ensure_covariances(c)) return rc;
-    if (int rc = build_voxelmap(c)) return rc;
+    c->stream = b->setup_streams[i % S];
+    if ((rc_setup = check_grid(c)) == RG_OK && (rc_setup = ensure_covariances(c)) == RG_OK) rc_setup = build_voxelmap(c);
+    c->stream = b->stream;
   }
+  for (int si = 0; si < S; si++) {
+    cudaEventRecord(b->setup_events[si], b->setup_streams[si]);
+    cudaStreamWaitEvent(b->stream, b->setup_events[si], 0);
+  }
+  if (rc_setup != RG_OK) return rc_setup;
   for (int i = 0; i < P; i++) {
     rg_ctx* c = b->pairs[i];
     if (int rc = prepare_linearize(c)) return rc;
