@@ -202,6 +202,13 @@ int rg_feature_extraction(rg_ctx*, const float* extracted_xyzi, const int32_t* p
                           const rg_feature_params* p, float* curvature, int32_t* neighbor_picked, int32_t* label,
                           float* corner_xyzi, int32_t* n_corner, float* surface_xyzi, int32_t* n_surface);
 
+/* One streamed front-end frame, device-resident end to end (BASELINE config 5): raw driver points (host) ->
+ * projectPointCloud/cloudExtraction -> calculateSmoothness/markOccludedPoints/extractFeatures -> the feature cloud
+ * `corner + surface` (lidarOdometry.cpp:521-524: featureLast = corner + surf) installed directly as this context's
+ * target (which = RG_TARGET) or source cloud. Only the two counts cross back to the host. */
+int rg_front_end_frame(rg_ctx*, const void* host_raw_points, size_t n_points, const rg_projection_params* pp,
+                       const rg_feature_params* fp, int which, int32_t* n_corner, int32_t* n_surface);
+
 #ifdef __cplusplus
 }
 #endif

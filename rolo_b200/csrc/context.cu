@@ -1225,3 +1225,67 @@ int rg_feature_extraction(rg_ctx* c, const float* extracted, const int32_t* col_
 }
 
 }  // extern "C"
+
+__global__ void concat_clouds_kernel(const float4* __restrict__ a, int na, const float4* __restrict__ b, int nb, int n_pad, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
+  if (i < na) p = a[i]; else if (i < na + nb) p = b[i - na];
+  p.w = 1.f;
+  out[i] = p;
+}
+
+extern "C" int rg_front_end_frame(rg_ctx* c, const void* raw, size_t n_points, const rg_projection_params* pp, const rg_feature_params* fp, int which,
+                                  int32_t* n_corner, int32_t* n_surface) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (!pp || !fp || (!raw && n_points)) return set_err(c, RG_ERR_INVALID, "rg_front_end_frame: null argument");
+  if (pp->n_scan != fp->n_scan || pp->horizon_scan != fp->horizon_scan || pp->n_scan < 1 || pp->horizon_scan < 1 || pp->downsample_rate < 1 ||
+      pp->point_stride_bytes < 12 || pp->point_stride_bytes % 4 || pp->ring_offset_bytes < 0 || pp->ring_offset_bytes + 2 > pp->point_stride_bytes ||
+      !(fp->surf_leaf_size > 0.f))
+    return set_err(c, RG_ERR_INVALID, "rg_front_end_frame: bad parameters");
+  if (pp->horizon_scan > FE_RING_CAP) return set_err(c, RG_ERR_UNSUPPORTED, "rg_front_end_frame: horizon_scan above the per-ring capacity (2048)");
+  if (int rc = fe_alloc(c, pp->n_scan, pp->horizon_scan)) return rc;
+  const int cells = pp->n_scan * pp->horizon_scan;
+  RG_CUDA(c, c->fe_raw.ensure(c->device, std::max<size_t>(n_points * pp->point_stride_bytes, 16)));
+  if (n_points) RG_CUDA(c, cudaMemcpyAsync(c->fe_raw.p, raw, n_points * pp->point_stride_bytes, cudaMemcpyHostToDevice, c->stream));
+  RG_CUDA(c, cudaMemsetAsync(c->fe_counts.p, 0, 8 * sizeof(int), c->stream));
+  ProjLaunch P;
+  P.raw = c->fe_raw.p; P.n_points = (int)n_points; P.stride = pp->point_stride_bytes; P.ring_offset = pp->ring_offset_bytes;
+  P.n_scan = pp->n_scan; P.horizon = pp->horizon_scan; P.downsample = pp->downsample_rate; P.min_range = pp->lidar_min_range; P.max_range = pp->lidar_max_range;
+  P.owner = c->fe_owner.p; P.range_image = c->fe_range_image.p; P.full = c->fe_full.p; P.row_count = c->fe_row_count.p;
+  P.extracted = c->fe_extracted.p; P.col_ind = c->fe_col.p; P.point_range = c->fe_prange.p; P.start_ring = c->fe_start.p; P.end_ring = c->fe_end.p;
+  P.n_extracted = c->fe_counts.p;
+  RG_CUDA(c, launch_projection(P, c->stream));
+  FeatLaunch F;
+  F.extracted = c->fe_extracted.p; F.col_ind = c->fe_col.p; F.point_range = c->fe_prange.p; F.start_ring = c->fe_start.p; F.end_ring = c->fe_end.p;
+  F.n_dev = c->fe_counts.p; F.n = cells; F.n_scan = fp->n_scan; F.horizon = fp->horizon_scan;
+  F.edge_thr = fp->edge_threshold; F.surf_thr = fp->surf_threshold; F.leaf = fp->surf_leaf_size;
+  F.curvature = c->fe_curv.p; F.picked = c->fe_picked.p; F.label = c->fe_label.p;
+  F.corner_ring = c->fe_corner_ring.p; F.corner_cnt = c->fe_corner_cnt.p; F.surf_ring = c->fe_surf_ring.p; F.surf_cnt = c->fe_surf_cnt.p;
+  F.corner_out = c->fe_corner_out.p; F.n_corner = c->fe_counts.p + 1; F.surf_out = c->fe_surf_out.p; F.n_surf = c->fe_counts.p + 2;
+  F.error_flag = c->fe_counts.p + 3;
+  RG_CUDA(c, launch_features(F, c->stream));
+  g_launches += 10;
+  int h[4] = {0, 0, 0, 0};
+  RG_CUDA(c, cudaMemcpyAsync(h, c->fe_counts.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (h[3] != 0) return set_err(c, RG_ERR_UNSUPPORTED, "rg_front_end_frame: sector/ring capacity exceeded");
+  if (n_corner) *n_corner = h[1];
+  if (n_surface) *n_surface = h[2];
+  Cloud& cl = which == RG_SOURCE ? c->src : c->tgt;
+  const int n = h[1] + h[2];
+  const int n_pad = (n + TILE_PTS - 1) / TILE_PTS * TILE_PTS;
+  RG_CUDA(c, cl.pts.ensure(c->device, std::max(n_pad, TILE_PTS)));
+  RG_CUDA(c, cl.cov6.ensure(c->device, (size_t)std::max(n_pad, TILE_PTS) * COV_PLANES));
+  cl.n = n; cl.n_pad = n_pad; cl.has_cov = false; cl.host_identity = nullptr;
+  if (n > 0) {
+    g_launches++;
+    concat_clouds_kernel<<<(n_pad + 255) / 256, 256, 0, c->stream>>>(c->fe_corner_out.p, h[1], c->fe_surf_out.p, h[2], n_pad, cl.pts.p);
+    RG_CUDA(c, cudaGetLastError());
+  }
+  if (which == RG_TARGET) c->voxel_ok = false;
+  c->st_ok = false; c->have_corr = false;
+  if (which == RG_SOURCE) c->shard_lo = c->shard_hi = 0;
+  return RG_OK;
+}

@@ -230,6 +230,18 @@ class RotVGICP:
     def lastKernelUs(self): return self._L.rg_last_kernel_us(self._h)
     def stream(self): return self._L.rg_stream(self._h)
 
+    def frontEndFrame(self, raw, which, n_scan=128, horizon_scan=2048, downsample_rate=1, lidar_min_range=2.0, lidar_max_range=1000.0,
+                      edge_threshold=0.8, surf_threshold=0.1, surf_leaf_size=0.4):
+        """Raw driver frame -> range image -> features -> `corner + surface` installed as this object's target/source cloud,
+        all on the device (imageProjection.cpp:399-505, featureExtraction.cpp:87-266, lidarOdometry.cpp:521-524)."""
+        raw = np.ascontiguousarray(raw)
+        pp = capi.ProjectionParams(n_scan, horizon_scan, downsample_rate, lidar_min_range, lidar_max_range, raw.dtype.itemsize, 20)
+        fp = capi.FeatureParams(n_scan, horizon_scan, edge_threshold, surf_threshold, surf_leaf_size)
+        nc = C.c_int32(); ns = C.c_int32()
+        self._ck(self._L.rg_front_end_frame(self._h, C.c_void_p(raw.ctypes.data), raw.shape[0], C.byref(pp), C.byref(fp), which, C.byref(nc), C.byref(ns)))
+        self._keep[which] = None
+        return nc.value, ns.value
+
     def setSourceShard(self, lo: int, hi: int): self._ck(self._L.rg_set_source_shard(self._h, lo, hi))
 
     def setReduceHook(self, fn, on_device: bool):

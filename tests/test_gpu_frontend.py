@@ -50,3 +50,33 @@ def test_projection_filters_and_first_writer_wins():
     assert pg["extracted"][0][0] == 10.0      # the first of the two competing points won
     fe2 = FrontEnd(n_scan=n_scan, horizon_scan=horizon, downsample_rate=2)
     assert fe2.image_projection(raw)["n"] == ob.image_projection(raw, n_scan, horizon, downsample_rate=2)["n"] == 1
+
+
+def test_streamed_front_end_matches_oracle_chain():
+    """BASELINE config 5 at small size: raw frame -> projection -> features -> `corner + surface` installed on the device
+    -> SO3-LM align + translation LM; every frame's pose must match the CPU oracle running the same three stages."""
+    from rolo_b200 import capi
+    from rolo_b200.registration import RotVGICP
+    sensor, rings, cols = "small", 32, 512
+    scene = synth.make_scene()
+    poses = [synth.pose((0.0, 0.0, 0.3 * k), (0.06 * k, 0.01 * k, 0.0)) for k in range(4)]
+    raws = [synth.raw_frame(scene, poses[k], sensor, seed=100 + k) for k in range(4)]
+    r = RotVGICP(); r.setPolarResolution(0.175, 0.175, 2.0)
+    r.frontEndFrame(raws[0], capi.TARGET, n_scan=rings, horizon_scan=cols)
+    prev = None
+    for k in range(4):
+        p = ob.image_projection(raws[k], rings, cols); f = ob.feature_extraction(p, rings, cols)
+        cur = np.concatenate([f["corner"], f["surface"]], axis=0)
+        if k > 0:
+            r.swapSourceAndTarget()
+            nc, ns = r.frontEndFrame(raws[k], capi.TARGET, n_scan=rings, horizon_scan=cols)
+            assert (nc, ns) == (len(f["corner"]), len(f["surface"]))
+            T = r.align()
+            t = r.computeTranslation(np.zeros(3), T[:3, 3].astype(np.float64), np.zeros(3), 0.1, 0.1, 0.3)
+            o = ob.Oracle(); o.setPolarResolution(0.175, 0.175, 2.0); o.setInputTarget(cur); o.setInputSource(prev)
+            To = o.align()
+            to = o.computeTranslation(np.zeros(3), To[:3, 3].astype(np.float64), np.zeros(3), 0.1, 0.1, 0.3)
+            drot, _ = synth.pose_error(o.getFinalPoseDouble(), r.getFinalPoseDouble())
+            assert drot <= 1e-4 and np.max(np.abs(t - to)) <= 1e-4
+            assert r.nrIterations() == o.nrIterations()
+        prev = cur
