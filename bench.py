@@ -13,8 +13,9 @@ resident in HBM; `e2e` goes through the C-ABI with host (pinned) buffers, H2D in
 Per step the inputs are re-installed, so covariances/voxel maps are recomputed every step (the
 reference's caller constructs a fresh object per frame, lidarOdometry.cpp:460).
 
---impl reference times the CPU oracle port of the reference algorithm (the reference itself cannot be
-built in this image: PCL/Eigen/Boost absent) with all host threads on the same workload.
+--impl reference times the reference's CPU/OpenMP implementation on the host cores: oracle/_ref (the reference's own
+rot_gicp sources compiled against oracle/ref_shim, since PCL/Eigen/Boost are absent from the image) when it was built,
+else the oracle port; same workload per registration.
 """
 from __future__ import annotations
 
@@ -113,6 +114,15 @@ def offsets_for(rank: int, pairs: int):
     return [synth.random_offset(rng) for _ in range(pairs)]
 
 
+def cpu_arm():
+    """(object, kind): oracle/_ref — the reference's own rot_gicp sources compiled against oracle/ref_shim — when it was
+    built (it needs /root/reference at build time; the .so travels), else the oracle port."""
+    from oracle import binding as ob
+    if ob.ref_available():
+        return ob.Reference(), "reference"
+    return ob.Oracle(), "port"
+
+
 def pick_threads(o, pair):
     """All host threads the CPU arm can use: os.cpu_count() (torchrun exports OMP_NUM_THREADS=1, so the OpenMP default
     is not trusted); if half as many threads (physical cores on an SMT host) is faster on one registration, use that."""
@@ -137,7 +147,7 @@ def run_reference(args, rank, world):
     scene = synth.make_scene()
     Ts = offsets_for(0, 2)
     clouds = [(synth.scan(scene, np.eye(4), SENSOR, seed=1234 + i), synth.scan(scene, Ts[i], SENSOR, seed=5678 + i)) for i in range(2)]
-    o = ob.Oracle()
+    o, kind = cpu_arm()
     o.setPolarResolution(*POLAR); o.setOptimizerType(ob.OPT_GAUSS_NEWTON); o.setMaximumIterations(GN_ITERS)
     o.setRotationEpsilon(1e-30); o.setTransformationEpsilon(1e-30)
     cores = pick_threads(o, clouds[0])
@@ -159,10 +169,10 @@ def run_reference(args, rank, world):
         "value": val, "unit": "registrations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: one 128x2048 OS1-128 scan pair per step, GaussNewton x20, CPU oracle port (OpenMP)",
+        "config": {"workload": "configs[1]: one 128x2048 OS1-128 scan pair per step, GaussNewton x20, CPU/OpenMP: " + ("the reference's own rot_gicp sources (oracle/_ref, shim Eigen/PCL)" if kind == "reference" else "oracle port"),
                    "points_per_cloud": N_POINTS, "gn_iters": GN_ITERS},
         "gn_iters_per_s": val * GN_ITERS,
-        "cpu_baseline": {"value": val, "unit": "registrations/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "registrations/s", "cores": cores, "kind": kind,
                          "sample": f"{args.steps} full registrations (1 per step) after {args.warmup} warm-ups"},
         "e2e": {"value": val, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -172,7 +182,7 @@ def run_reference(args, rank, world):
 def cpu_baseline_sample(clouds_host):
     """Bounded CPU sample on rank 0: a few full registrations with the oracle port (reported, not a target)."""
     from oracle import binding as ob
-    o = ob.Oracle()
+    o, kind = cpu_arm()
     o.setPolarResolution(*POLAR); o.setOptimizerType(ob.OPT_GAUSS_NEWTON); o.setMaximumIterations(GN_ITERS)
     o.setRotationEpsilon(1e-30); o.setTransformationEpsilon(1e-30)
     cores = pick_threads(o, clouds_host[0])
@@ -188,7 +198,7 @@ def cpu_baseline_sample(clouds_host):
         if time.perf_counter() - t0 > 12.0 or n >= 8:
             break
     dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "registrations/s", "cores": cores, "kind": "port",
+    return {"value": n / dt, "unit": "registrations/s", "cores": cores, "kind": kind,
             "sample": f"{n} full 128x2048 registrations (covariances + voxel map + {GN_ITERS} GN iters), {dt:.1f} s of CPU work"}, poses
 
 

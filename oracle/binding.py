@@ -260,3 +260,126 @@ def feature_extraction(proj: dict, n_scan, horizon, edge_threshold=0.8, surf_thr
     L.ro_feature_extraction(vp(ext), vp(col), vp(rng), vp(st), vp(en), C.c_int(n), C.c_int(n_scan), C.c_int(horizon), C.c_float(edge_threshold),
                             C.c_float(surf_threshold), C.c_float(surf_leaf_size), vp(curv), vp(picked), vp(label), vp(corner), C.byref(nc), vp(surf), C.byref(ns))
     return {"curvature": curv, "neighbor_picked": picked, "label": label, "corner": corner[:nc.value].copy(), "surface": surf[:ns.value].copy()}
+
+
+# ---- oracle/_ref: the REFERENCE's own rot_gicp sources compiled against oracle/ref_shim (see oracle/Makefile) ----
+_REF_PATH = os.path.join(_HERE, "_ref", "librolo_ref.so")
+_ref = None
+
+
+def ref_available() -> bool:
+    return os.path.exists(_REF_PATH)
+
+
+def build_ref() -> str | None:
+    """Compiles the reference's rot_gicp headers from /root/reference (only possible where that checkout exists)."""
+    if not os.path.isdir("/root/reference/include/rot_gicp"):
+        return _REF_PATH if os.path.exists(_REF_PATH) else None
+    subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    return _REF_PATH
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        L = C.CDLL(_REF_PATH)
+        L.rr_create.restype = C.c_void_p
+        for name in ("rr_linearize", "rr_so3_linearize", "rr_compute_error", "rr_t3_linearize", "rr_compute_t_error"):
+            getattr(L, name).restype = C.c_double
+        for name in ("rr_get_covariances", "rr_num_correspondences"):
+            getattr(L, name).restype = C.c_size_t
+        _ref = L
+    return _ref
+
+
+class Reference:
+    """fast_gicp::RotVGICP<PointXYZI, PointXYZI> of the reference itself (oracle/ref_driver.cpp); same methods as Oracle."""
+
+    def __init__(self):
+        self.L = ref_lib()
+        self.h = C.c_void_p(self.L.rr_create())
+
+    def __del__(self):
+        try:
+            self.L.rr_destroy(self.h)
+        except Exception:
+            pass
+
+    def setNumThreads(self, n): self.L.rr_set_num_threads(self.h, C.c_int(n))
+    def setResolution(self, r): self.L.rr_set_resolution(self.h, C.c_double(r))
+    def setPolarResolution(self, a, b, c): self.L.rr_set_polar_resolution(self.h, C.c_double(a), C.c_double(b), C.c_double(c))
+    def setNeighborSearchMethod(self, m): self.L.rr_set_neighbor_search_method(self.h, C.c_int(m))
+    def setRegularizationMethod(self, m): self.L.rr_set_regularization_method(self.h, C.c_int(m))
+    def setCorrespondenceRandomness(self, k): self.L.rr_set_correspondence_randomness(self.h, C.c_int(k))
+    def setOptimizerType(self, t): self.L.rr_set_optimizer_type(self.h, C.c_int(t))
+    def setMaximumIterations(self, n): self.L.rr_set_max_iterations(self.h, C.c_int(n))
+    def setRotationEpsilon(self, e): self.L.rr_set_rotation_epsilon(self.h, C.c_double(e))
+    def setTransformationEpsilon(self, e): self.L.rr_set_transformation_epsilon(self.h, C.c_double(e))
+
+    def setInputSource(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        self.L.rr_set_input_source(self.h, pts.ctypes.data_as(_fp), C.c_size_t(pts.shape[0]), C.c_size_t(pts.shape[1]))
+
+    def setInputTarget(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float32)
+        self.L.rr_set_input_target(self.h, pts.ctypes.data_as(_fp), C.c_size_t(pts.shape[0]), C.c_size_t(pts.shape[1]))
+
+    def calculateCovariances(self, which): return self.L.rr_calculate_covariances(self.h, C.c_int(which))
+
+    def getCovariances(self, which):
+        n = self.L.rr_get_covariances(self.h, C.c_int(which), None)
+        out = np.empty((n, 4, 4)); self.L.rr_get_covariances(self.h, C.c_int(which), _d(out)); return out
+
+    def getSourceCovariances(self): return self.getCovariances(0)
+    def getTargetCovariances(self): return self.getCovariances(1)
+
+    def _set_covs(self, which, covs):
+        covs = np.ascontiguousarray(covs, dtype=np.float64).reshape(-1, 16)
+        self.L.rr_set_covariances(self.h, C.c_int(which), _d(covs), C.c_size_t(covs.shape[0]))
+
+    def setSourceCovariances(self, c): self._set_covs(0, c)
+    def setTargetCovariances(self, c): self._set_covs(1, c)
+
+    def linearize(self, T):
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(16); H = np.empty((6, 6)); b = np.empty(6)
+        return self.L.rr_linearize(self.h, _d(T), _d(H), _d(b)), H, b
+
+    def so3_linearize(self, T):
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(16); H = np.empty((3, 3)); b = np.empty(3)
+        return self.L.rr_so3_linearize(self.h, _d(T), _d(H), _d(b)), H, b
+
+    def compute_error(self, T):
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+        return self.L.rr_compute_error(self.h, _d(T))
+
+    def t3_linearize(self, t, g, l, dtn, dtn1):
+        t, g, l = (np.ascontiguousarray(x, dtype=np.float64) for x in (t, g, l)); H = np.empty((6, 6)); b = np.empty(6)
+        return self.L.rr_t3_linearize(self.h, _d(t), _d(g), _d(l), C.c_double(dtn), C.c_double(dtn1), _d(H), _d(b)), H, b
+
+    def compute_t_error(self, t, g, l, dtn, dtn1):
+        t, g, l = (np.ascontiguousarray(x, dtype=np.float64) for x in (t, g, l))
+        return self.L.rr_compute_t_error(self.h, _d(t), _d(g), _d(l), C.c_double(dtn), C.c_double(dtn1))
+
+    def setCtLambda(self, lam): self.L.rr_set_ct_lambda(self.h, C.c_float(lam))
+    def numCorrespondences(self): return self.L.rr_num_correspondences(self.h)
+
+    def align(self, guess=None):
+        g = np.eye(4, dtype=np.float32) if guess is None else np.ascontiguousarray(guess, dtype=np.float32)
+        out = np.empty((4, 4), dtype=np.float32)
+        self.L.rr_align(self.h, g.ctypes.data_as(_fp), out.ctypes.data_as(_fp))
+        self.final_transformation = out
+        return out
+
+    def getFinalPoseDouble(self):
+        return self.final_transformation.astype(np.float64)   # the reference only keeps the float32 matrix
+
+    def computeTranslation(self, trans, g, l, dtn, dtn1, lam):
+        t = np.array(trans, dtype=np.float64); g, l = (np.ascontiguousarray(x, dtype=np.float64) for x in (g, l))
+        self.L.rr_compute_translation(self.h, _d(t), _d(g), _d(l), C.c_double(dtn), C.c_double(dtn1), C.c_float(lam))
+        return t
+
+    def hasConverged(self): return bool(self.L.rr_has_converged(self.h))
+    def nrIterations(self): return self.L.rr_nr_iterations(self.h)
+
+    def getFinalHessian(self):
+        H = np.empty((6, 6)); self.L.rr_get_final_hessian(self.h, _d(H)); return H

@@ -6,10 +6,11 @@
 // "lsq.hpp" = include/rot_gicp/gicp/impl/lsq_registration_impl.hpp,
 // "voxel.hpp" = include/rot_gicp/gicp/vmp_voxel.hpp, "so3.hpp" = include/rot_gicp/so3/so3.hpp.
 //
-// PARITY UNPINNED BY THE REFERENCE: it ships no golden vectors for this path and cannot be
-// built here (needs PCL/Eigen/Boost, absent). Third-party arithmetic restated from the
-// published algorithms: Eigen 3.3+ JacobiSVD (two-sided Jacobi), Eigen LDLT (diagonal
-// pivoting), Eigen fixed-size 4x4 inverse (cofactors), PCL/FLANN exact kNN with float L2.
+// PINNING: the reference ships no golden vectors for this path; this restatement is checked against the
+// reference's own sources compiled here (oracle/_ref, tests/test_oracle_vs_ref_cpu.py, agreement 1e-11).
+// Third-party arithmetic absent from the tree stays restated from the published algorithms: Eigen 3.3+
+// JacobiSVD (two-sided Jacobi), Eigen LDLT (diagonal pivoting), Eigen fixed-size 4x4 inverse (cofactors),
+// PCL/FLANN exact kNN with float L2.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may
 // load this library. The product (rolo_b200/) never does.
@@ -698,7 +699,9 @@ struct ro_ctx {
     }
     double w = std::sqrt((double)c.second->num_points);
     const M4& Mh = mahalanobis[i];
-    double val = w * (quad4(error, Mh) + (double)lambda_ / (double)pt_size * quad4(ct, Mh));
+    // `lambda_/pt_size` is float / size_t: a FLOAT division in the reference (impl.hpp:555,653), promoted afterwards
+    const double lam = (double)(lambda_ / (float)pt_size);
+    double val = w * (quad4(error, Mh) + lam * quad4(ct, Mh));
     if (transed_out) *transed_out = transed;
     if (error_out) *error_out = error;
     if (ct_out) *ct_out = ct;
@@ -724,7 +727,7 @@ struct ro_ctx {
       for (int r = 0; r < 3; r++) for (int cc = 0; cc < 3; cc++) J1[r*6+cc] = S[r*3+cc];
       for (int r = 0; r < 3; r++) J1[r*6+3+r] = -1.0;
       double J2[4*6]; for (int k = 0; k < 24; k++) J2[k] = 1.0 / dtn * J1[k];     // impl.hpp:579
-      const double lam = (double)lambda_ / (double)pt_size;
+      const double lam = (double)(lambda_ / (float)pt_size);   // float division, impl.hpp:582,584
       double MJ1[24], MJ2[24], Me[4], Mct[4];
       for (int r = 0; r < 4; r++) for (int cc = 0; cc < 6; cc++) {
         double s1 = 0, s2 = 0;

@@ -10,10 +10,15 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs may load it.  Nothing under rolo_b200/ links or imports it.
  *
- * PARITY UNPINNED BY THE REFERENCE: the reference ships no golden vectors or
- * numeric tests for this path and cannot be compiled in this
- * image without its external libraries (PCL/Eigen/Boost absent).  See
- * oracle/README.md for how the restatement is pinned instead.
+ * PINNING: the reference ships no golden vectors or numeric tests for this path
+ * (SURVEY.md §4, §8c). The restatement is pinned against the reference ITSELF run
+ * here: oracle/_ref/librolo_ref.so is the reference's own rot_vgicp_impl.hpp /
+ * lsq_registration_impl.hpp / vmp_voxel.hpp / so3.hpp compiled from /root/reference
+ * (oracle/ref_driver.cpp, `make -C oracle ref`) and tests/test_oracle_vs_ref_cpu.py
+ * requires covariances, per-call {H,b,cost}, align() and computeTranslation() to agree
+ * to 1e-11. What stays restated (not pinned by reference code, absent from the tree):
+ * Eigen's JacobiSVD/LDLT/inverse and PCL/FLANN's kNN, provided by oracle/ref_shim for
+ * both sides.
  *
  * Conventions: all matrices ROW-MAJOR. Poses are 4x4 (double[16]).
  * H6 is 6x6 row-major (36 doubles), b6 6 doubles; H3 3x3 (9), b3 (3).

@@ -531,8 +531,8 @@ int make_dyn(rg_ctx* c, const host::Request& r, const double* t3_guess, const do
       d.ct[0] = -(t3_guess[0] + r.t[0]) / dtn - lx / dtn1;
       d.ct[1] = -(t3_guess[1] + r.t[1]) / dtn;
       d.ct[2] = -(t3_guess[2] + r.t[2]) / dtn;
-      const double pt_size = (double)c->num_corr;
-      d.lam_c = (double)c->lambda_ / pt_size;                                   // impl.hpp:555,582
+      // `lambda_/pt_size` is float / size_t in the reference: a float division, promoted to double afterwards (impl.hpp:555,582)
+      d.lam_c = (double)(c->lambda_ / (float)c->num_corr);
       d.h_scale = 1.0 + d.lam_c / (dtn * dtn);
       d.b_ct_scale = d.lam_c / dtn;
       mode = (r.kind == host::REQ_T3_LIN) ? LIN_SE3 : LIN_COST; refresh = 0;
