@@ -316,7 +316,7 @@ GridParams make_grid(const rg_ctx* c) {
 int upload_cloud(rg_ctx* c, Cloud& cl, const float* host, size_t n, size_t stride_bytes) {
   if (use_device(c)) return RG_ERR_CUDA;
   if (n > 0 && !host) return set_err(c, RG_ERR_INVALID, "null cloud pointer");
-  if (stride_bytes < 12 || stride_bytes % 4) return set_err(c, RG_ERR_INVALID, "stride_bytes must be a multiple of 4 and >= 12");
+  if (n > 0 && (stride_bytes < 12 || stride_bytes % 4)) return set_err(c, RG_ERR_INVALID, "stride_bytes must be a multiple of 4 and >= 12");
   if (n > (size_t)1 << 30) return set_err(c, RG_ERR_INVALID, "cloud too large");
   const int n_pad = (int)((n + TILE_PTS - 1) / TILE_PTS * TILE_PTS);
   RG_CUDA(c, cl.pts.ensure(c->device, std::max(n_pad, TILE_PTS)));

@@ -230,18 +230,23 @@ linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict_
         const double c0 = v1.y + ca0, c1 = v2.x + ca1, c2 = v2.y + ca2, c3 = v3.x + ca3, c4 = v3.y + ca4, c5 = v4.x + ca5;
         const double w = v4.y;
 
-        // M = C^-1 by cofactors (symmetric)
-        const double k0 = c3 * c5 - c4 * c4;
-        const double k1 = c2 * c4 - c1 * c5;
-        const double k2 = c1 * c4 - c2 * c3;
-        const double det = c0 * k0 + c1 * k1 + c2 * k2;
-        const double idet = 1.0 / det;
-        const double m0 = k0 * idet, m1 = k1 * idet, m2 = k2 * idet;
-        const double m3 = (c0 * c5 - c2 * c2) * idet;
-        const double m4 = (c1 * c2 - c0 * c4) * idet;
-        const double m5 = (c0 * c3 - c1 * c1) * idet;
+        // M = C^-1 = adj(C) / det. Every sum is linear in M, so all products are formed on the adjugate and the
+        // reciprocal of the determinant is folded into the weights: the division (rcp.approx + 2 Newton steps, no
+        // branchy IEEE slow path) leaves the critical path and overlaps the Jacobian products.
+        const double m0 = c3 * c5 - c4 * c4;
+        const double m1 = c2 * c4 - c1 * c5;
+        const double m2 = c1 * c4 - c2 * c3;
+        const double m3 = c0 * c5 - c2 * c2;
+        const double m4 = c1 * c2 - c0 * c4;
+        const double m5 = c0 * c3 - c1 * c1;
+        const double det = c0 * m0 + c1 * m1 + c2 * m2;
+        double idet;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(idet) : "d"(det));
+        idet = fma(idet, fma(-det, idet, 1.0), idet);
+        idet = fma(idet, fma(-det, idet, 1.0), idet);
+        const double wi = w * idet;                       // weight of terms built on adj(C)
 
-        // residuals
+        // residuals (on the adjugate)
         const double ex = mx - x, ey = my - y, ez = mz - z;
         const double qx = m0 * ex + m1 * ey + m2 * ez;
         const double qy = m1 * ex + m3 * ey + m4 * ez;
@@ -249,7 +254,7 @@ linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict_
         double cost = ex * qx + ey * qy + ez * qz;
         // continuous-time term (t3 modes; lam_c = 0 otherwise)  rot_vgicp_impl.hpp:548,555
         const double lam_c = s_dyn.lam_c;
-        double bx = qx, by = qy, bz = qz;      // M e_b with e_b = e + b_ct_scale * ct
+        double bx = qx, by = qy, bz = qz;      // adj(C) e_b with e_b = e + b_ct_scale * ct
         if (lam_c != 0.0) {
           const double tx = s_dyn.ct[0], ty = s_dyn.ct[1], tz = s_dyn.ct[2];
           const double ux = m0 * tx + m1 * ty + m2 * tz;
@@ -260,10 +265,10 @@ linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict_
         }
 
         if (MODE == LIN_COST) {
-          acc[0] += w * cost;
+          acc[0] += wi * cost;
           acc[1] += 1.0;
         } else {
-          const double ws = w * s_dyn.h_scale;
+          const double ws = wi * s_dyn.h_scale;
           // G = M S, S = skew(p') = [[0,-z,y],[z,0,-x],[-y,x,0]]
           const double g00 = m1 * z - m2 * y, g01 = m2 * x - m0 * z, g02 = m0 * y - m1 * x;
           const double g10 = m3 * z - m4 * y, g11 = m4 * x - m1 * z, g12 = m1 * y - m3 * x;
@@ -280,14 +285,14 @@ linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict_
             acc[9] += ws * g10; acc[10] += ws * g11; acc[11] += ws * g12;
             acc[12] += ws * g20; acc[13] += ws * g21; acc[14] += ws * g22;
             acc[15] += ws * h00; acc[16] += ws * h01; acc[17] += ws * h02; acc[18] += ws * h11; acc[19] += ws * h12; acc[20] += ws * h22;
-            acc[21] += w * bx; acc[22] += w * by; acc[23] += w * bz;
-            acc[24] += w * sx; acc[25] += w * sy; acc[26] += w * sz;
-            acc[27] += w * cost;
+            acc[21] += wi * bx; acc[22] += wi * by; acc[23] += wi * bz;
+            acc[24] += wi * sx; acc[25] += wi * sy; acc[26] += wi * sz;
+            acc[27] += wi * cost;
             acc[28] += 1.0;
           } else {
             acc[0] += ws * h00; acc[1] += ws * h01; acc[2] += ws * h02; acc[3] += ws * h11; acc[4] += ws * h12; acc[5] += ws * h22;
-            acc[6] += w * sx; acc[7] += w * sy; acc[8] += w * sz;
-            acc[9] += w * cost;
+            acc[6] += wi * sx; acc[7] += wi * sy; acc[8] += wi * sz;
+            acc[9] += wi * cost;
             acc[10] += 1.0;
           }
         }

@@ -1,0 +1,128 @@
+"""GPU edge cases the domain offers: ragged sizes (not multiples of the 256-point TMA tile), tiny clouds, unequal cloud
+sizes, k variants incl. the >32 fallback, empty inputs, out-of-range keys, swap/clear/caller-supplied covariances, and
+size-independent properties (linearity of the sums over a source partition, invariance to point order)."""
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from rolo_b200 import capi, synth
+from rolo_b200.registration import RotVGICP
+
+from helpers import make_both, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _sub(cloud, n, seed):
+    rng = np.random.default_rng(seed)
+    return np.ascontiguousarray(cloud[np.sort(rng.choice(cloud.shape[0], size=n, replace=False))])
+
+
+@pytest.mark.parametrize("n_tgt,n_src", [(1000, 777), (257, 255), (300, 4096), (4096, 31), (21, 20)])
+def test_ragged_sizes(small_pair, n_tgt, n_src):
+    tgt, src, T_gt = small_pair
+    t = _sub(tgt, n_tgt, 1); s = _sub(src, n_src, 2)
+    o, g = make_both(t, s, uniform=2.0, method=capi.DIRECT27, shared_covs=False)
+    assert np.array_equal(o.knn(0, 20), g.knn(capi.SOURCE, 20)) and np.array_equal(o.knn(1, 20), g.knn(capi.TARGET, 20))
+    o.calculateCovariances(0); o.calculateCovariances(1)
+    cs = o.getSourceCovariances().astype(np.float32).astype(np.float64); ct = o.getTargetCovariances().astype(np.float32).astype(np.float64)
+    for x in (o, g):
+        x.setSourceCovariances(cs); x.setTargetCovariances(ct)
+    for T in (np.eye(4), T_gt):
+        co, Ho, bo = o.linearize(T); cg, Hg, bg = g.linearize(T)
+        assert g.numCorrespondences() == len(o.getCorrespondences()[0])
+        if co != 0:
+            assert rel_err(cg, co) <= 1e-9 and rel_err(Hg, Ho) <= 1e-9 and rel_err(bg, bo) <= 1e-9 * max(1.0, np.abs(Ho).max() / max(np.abs(bo).max(), 1e-300))
+    o2, g2 = make_both(t, s, shared_covs=False)
+    for x in (o2, g2):
+        x.setOptimizerType(capi.OPT_LM)
+    To = o2.align(); Tg = g2.align()
+    drot, dtr = synth.pose_error(o2.getFinalPoseDouble(), g2.getFinalPoseDouble())
+    assert drot <= 1e-4 and dtr <= 1e-4 and o2.nrIterations() == g2.nrIterations()
+
+
+@pytest.mark.parametrize("k", [3, 10, 20, 32, 33, 40])
+def test_k_variants(tiny_pair, k):
+    tgt, src, _ = tiny_pair
+    o, g = make_both(tgt, src, k=k, shared_covs=False)
+    assert np.array_equal(o.knn(1, k), g.knn(capi.TARGET, k))
+    if k < 4:
+        return    # 3 neighbours span a plane exactly: the smallest singular value is 0 and the sign of u3 v3^T is rounding noise
+                  # in the reference itself (JacobiSVD of a singular matrix), so only the neighbour sets are compared
+    o.calculateCovariances(0); g.calculate_covariances(capi.SOURCE)
+    assert np.max(np.abs(o.getSourceCovariances() - g.getSourceCovariances())) <= 3e-7
+
+
+def test_duplicate_points_tie_break():
+    """exact duplicates: equal float distances must be broken by the lower index on both sides"""
+    rng = np.random.default_rng(5)
+    base = rng.uniform(-5, 5, size=(300, 3)).astype(np.float32)
+    pts = np.concatenate([base, base[:100], base[:50]], axis=0)
+    cloud = np.concatenate([pts, np.ones((len(pts), 1), np.float32)], axis=1)
+    o, g = make_both(cloud, cloud.copy(), shared_covs=False)
+    assert np.array_equal(o.knn(1, 20), g.knn(capi.TARGET, 20))
+
+
+def test_empty_and_too_small_inputs(tiny_pair):
+    tgt, src, _ = tiny_pair
+    r = RotVGICP(); r.setPolarResolution(0.175, 0.175, 2.0)
+    with pytest.raises(ValueError):
+        r.align()                                                   # nothing set
+    r.setInputTarget(tgt); r.setInputSource(np.zeros((0, 4), np.float32))
+    with pytest.raises(ValueError):
+        r.align()                                                   # empty source
+    r.setInputSource(src[:10])
+    with pytest.raises(ValueError):
+        r.align()                                                   # fewer points than k (reference reads uninitialised memory here)
+    r.setCorrespondenceRandomness(5)
+    r.align()                                                       # now fine
+    far = src.copy(); far[:, :3] *= 1e7
+    r2 = RotVGICP(); r2.setResolution(1.0); r2.setInputTarget(far); r2.setInputSource(src)
+    with pytest.raises((ValueError, capi.RoloError)):
+        r2.align()                                                  # voxel keys beyond the +-2^20 range are reported, not wrapped
+
+
+def test_swap_clear_and_supplied_covariances(small_pair):
+    tgt, src, _ = small_pair
+    o, g = make_both(tgt, src)                                      # caller-supplied covariances on both sides
+    c1, H1, b1 = g.linearize(np.eye(4))
+    g.swapSourceAndTarget()
+    o2, _ = make_both(src, tgt)
+    co, Ho, bo = o2.linearize(np.eye(4)); cg, Hg, bg = g.linearize(np.eye(4))
+    assert rel_err(cg, co) <= 1e-9 and rel_err(Hg, Ho) <= 1e-9
+    g.swapSourceAndTarget()
+    c3, H3, b3 = g.linearize(np.eye(4))
+    assert c3 == c1 and np.array_equal(H3, H1)                      # deterministic: same launch shape, same sums
+    g.clearSource()
+    with pytest.raises(ValueError):
+        g.linearize(np.eye(4))
+
+
+def test_sums_are_linear_over_a_source_partition(c1_pair):
+    """size-independent property at full config-1 size: H, b, cost of the whole source = sum over tile-aligned shards."""
+    tgt, src, T_gt = c1_pair
+    g = RotVGICP(); g.setPolarResolution(0.175, 0.175, 2.0); g.setInputTarget(tgt); g.setInputSource(src)
+    c, H, b = g.linearize(T_gt)
+    parts = [(0, 20480), (20480, 40192), (40192, src.shape[0])]
+    cs, Hs, bs, ncorr = 0.0, np.zeros((6, 6)), np.zeros(6), 0
+    for lo, hi in parts:
+        g.setSourceShard(lo, hi)
+        ci, Hi, bi = g.linearize(T_gt)
+        cs += ci; Hs += Hi; bs += bi; ncorr += g.numCorrespondences()
+    g.setSourceShard(0, 0)
+    assert rel_err(cs, c) <= 1e-12 and rel_err(Hs, H) <= 1e-12 and rel_err(bs, b) <= 1e-10
+    g.linearize(T_gt)
+    assert ncorr == g.numCorrespondences()
+
+
+def test_point_order_invariance(small_pair):
+    """permuting the source changes only the summation order"""
+    tgt, src, T_gt = small_pair
+    o, g = make_both(tgt, src)
+    c, H, b = g.linearize(T_gt)
+    perm = np.random.default_rng(3).permutation(src.shape[0])
+    o2, g2 = make_both(tgt, np.ascontiguousarray(src[perm]), shared_covs=False)
+    cs = o.getSourceCovariances()[perm]
+    g2.setSourceCovariances(cs); g2.setTargetCovariances(o.getTargetCovariances())
+    c2, H2, b2 = g2.linearize(T_gt)
+    assert rel_err(c2, c) <= 1e-11 and rel_err(H2, H) <= 1e-11
