@@ -828,6 +828,7 @@ int rg_align(rg_ctx* c, const float guess[16], float out_T[16]) {
   if (guess) for (int i = 0; i < 16; i++) g[i] = (double)guess[i]; else host::mat4_identity(g);
   c->lsq.begin_align(g);
   if (int rc = run_driver(c, nullptr, nullptr, 0, 0)) return rc;
+  if (fetch_voxel_count(c) < 0) return RG_ERR_INVALID;               // target voxel keys outside the +-2^20 cell range are an error, not dropped
   for (int i = 0; i < 16; i++) out_T[i] = (float)c->lsq.x0[i];      // final_transformation_ = x0.cast<float>() (lsq.hpp:177)
   return c->lsq.failed ? RG_ERR_NOT_CONVERGED : RG_OK;
 }
@@ -1122,6 +1123,15 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
     }
   }
   int rc_all = RG_OK;
+  {   // voxel-key range / table overflow flags of all pairs: P small async copies, one sync
+    std::vector<int> flags((size_t)P * 2, 0);
+    for (int i = 0; i < P; i++) RG_CUDA(nullptr, cudaMemcpyAsync(&flags[(size_t)i * 2], b->pairs[i]->counters.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, b->stream));
+    RG_CUDA(nullptr, cudaStreamSynchronize(b->stream));
+    for (int i = 0; i < P; i++) {
+      b->pairs[i]->n_vox = flags[(size_t)i * 2];
+      if (flags[(size_t)i * 2 + 1] != 0) return set_err(b->pairs[i], RG_ERR_INVALID, "voxel coordinate out of the +-2^20 key range (or table overflow)");
+    }
+  }
   for (int i = 0; i < P; i++) {
     rg_ctx* c = b->pairs[i];
     for (int k = 0; k < 16; k++) out_T[i * 16 + k] = (float)c->lsq.x0[k];
