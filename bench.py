@@ -207,7 +207,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=16, help="scan pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=32, help="scan pairs per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -251,11 +251,14 @@ def main():
     ext = torch.cuda.ExternalStream(batch.stream(), device=dev)
 
     def step(resident: bool):
+        # per pair: install both clouds, then start the covariance estimation right away (it is part of align();
+        # starting it as soon as a pair's clouds are queued lets uploads and kNN kernels of different pairs overlap)
         for i in range(P):
             if resident:
                 batch[i].setInputTarget(tgt_dev[i]); batch[i].setInputSource(src_dev[i])
             else:
                 batch[i].setInputTarget(tgt_host[i]); batch[i].setInputSource(src_host[i])
+            batch[i].calculate_covariances(capi.TARGET); batch[i].calculate_covariances(capi.SOURCE)
         return batch.align()
 
     def barrier():

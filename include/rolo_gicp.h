@@ -82,7 +82,10 @@ int rg_set_debug_print(rg_ctx*, int on);                                   /* ls
 /* ---- clouds ------------------------------------------------------------------------------------ */
 /* setInputSource / setInputTarget (rot_vgicp_impl.hpp:111-120, 132-143). xyz are the first three
  * floats of each point; stride_bytes = sizeof(PointT) (32 for pcl::PointXYZI, 16 for PointXYZ).
- * The data is copied to the device (H2D on the context's stream) before the call returns.      */
+ * The H2D copy is queued on the context's stream: from pageable memory the host buffer is consumed before the call
+ * returns; from page-locked memory the copy is asynchronous and the buffer must stay valid and unmodified until the next
+ * solving call (rg_align, rg_linearize, rg_calculate_covariances, ...) has returned — pcl::Registration keeps the cloud's
+ * shared_ptr for exactly that long in the reference.                                               */
 int rg_set_input_source(rg_ctx*, const float* host_points, size_t n, size_t stride_bytes);
 int rg_set_input_target(rg_ctx*, const float* host_points, size_t n, size_t stride_bytes);
 /* same, from device-resident float4 (x,y,z,*) arrays: no host traffic */

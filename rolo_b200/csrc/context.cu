@@ -196,6 +196,9 @@ struct rg_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
+  cudaStream_t upload_stream = nullptr;   // H2D cloud uploads (== stream, or the pair's setup stream inside a batch)
+  cudaEvent_t ev_upload = nullptr;
+  bool side_pending = false;              // work queued on upload_stream that `stream` has not been ordered after yet
   mutable std::string err;
 
   // RotVGICP members (rot_vgicp_impl.hpp:20-39)
@@ -295,9 +298,14 @@ int set_err(const rg_ctx* c, int code, const std::string& msg) {
       return set_err(ctx, RG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
   } while (0)
 
-int use_device(const rg_ctx* c) {
+int use_device(const rg_ctx* cc) {
+  rg_ctx* c = const_cast<rg_ctx*>(cc);
   cudaError_t e = cudaSetDevice(c->device);
   if (e != cudaSuccess) return set_err(c, RG_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  if (c->side_pending && c->upload_stream && c->stream != c->upload_stream) {   // lazily order `stream` after side-stream work of this context
+    cudaStreamWaitEvent(c->stream, c->ev_upload, 0);
+    c->side_pending = false;
+  }
   return RG_OK;
 }
 
@@ -323,12 +331,23 @@ int upload_cloud(rg_ctx* c, Cloud& cl, const float* host, size_t n, size_t strid
   RG_CUDA(c, cl.cov6.ensure(c->device, (size_t)std::max(n_pad, TILE_PTS) * COV_PLANES));
   cl.n = (int)n; cl.n_pad = n_pad; cl.has_cov = false; cl.host_identity = host;
   if (n == 0) return RG_OK;
+  cudaStream_t us = c->upload_stream ? c->upload_stream : c->stream;
+  if (us != c->stream) {   // order after whatever the context queued before (e.g. the previous frame still using these buffers)
+    RG_CUDA(c, cudaEventRecord(c->ev_upload, c->stream));
+    RG_CUDA(c, cudaStreamWaitEvent(us, c->ev_upload, 0));
+  }
+  if (c->staging.cap < n * stride_bytes) RG_CUDA(c, cudaStreamSynchronize(us));   // about to re-allocate a buffer in-flight work may read
   RG_CUDA(c, c->staging.ensure(c->device, n * stride_bytes));
-  RG_CUDA(c, cudaMemcpyAsync(c->staging.p, host, n * stride_bytes, cudaMemcpyHostToDevice, c->stream));
+  // pageable memory: the runtime stages the copy before returning; page-locked memory: truly asynchronous, the caller keeps
+  // the cloud alive until the next solving call returns (pcl::Registration holds the cloud's shared_ptr, as in the reference)
+  RG_CUDA(c, cudaMemcpyAsync(c->staging.p, host, n * stride_bytes, cudaMemcpyHostToDevice, us));
   g_launches++;
-  extract_points_kernel<<<(n_pad + 255) / 256, 256, 0, c->stream>>>(c->staging.p, stride_bytes, (int)n, n_pad, cl.pts.p);
+  extract_points_kernel<<<(n_pad + 255) / 256, 256, 0, us>>>(c->staging.p, stride_bytes, (int)n, n_pad, cl.pts.p);
   RG_CUDA(c, cudaGetLastError());
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));   // contract: the host buffer is consumed before returning
+  if (us != c->stream) {
+    RG_CUDA(c, cudaEventRecord(c->ev_upload, us));
+    RG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_upload, 0));
+  }
   return RG_OK;
 }
 
@@ -443,7 +462,8 @@ int sm_count(int device) {
 int choose_blocks_per_pair(int device, int n, int n_pairs) {
   const int ntiles = std::max(1, (n + TILE_PTS - 1) / TILE_PTS);
   const int slots = sm_count(device) * 2;                     // 2 resident CTAs per SM (launch bounds)
-  int per_pair = std::max(1, (slots * 2 + n_pairs - 1) / n_pairs);   // ~2 waves of CTAs over the whole batch
+  static const int waves = [] { const char* e = getenv("ROLO_LIN_WAVES"); int w = e ? atoi(e) : 2; return (w >= 1 && w <= 16) ? w : 2; }();
+  int per_pair = std::max(1, (slots * waves) / n_pairs);             // whole waves of CTAs over the batch (never a ragged extra wave)
   if (n_pairs == 1) per_pair = slots;
   return std::min(ntiles, per_pair);
 }
@@ -647,6 +667,8 @@ static int create_ctx(int device, cudaStream_t shared_stream, rg_ctx** out) {
   if (shared_stream) { c->stream = shared_stream; c->own_stream = false; }
   else if ((e = pool().stream_get(device, &c->stream)) != cudaSuccess) { delete c; return set_err(nullptr, RG_ERR_CUDA, std::string("stream: ") + cudaGetErrorString(e)); }
   cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+  cudaEventCreateWithFlags(&c->ev_upload, cudaEventDisableTiming);
+  c->upload_stream = c->stream;
   *out = c;
   return RG_OK;
 }
@@ -656,6 +678,7 @@ int rg_create(int device, rg_ctx** out) { return create_ctx(device, nullptr, out
 void rg_destroy(rg_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->upload_stream && c->upload_stream != c->stream) cudaStreamSynchronize(c->upload_stream);
   cudaStreamSynchronize(c->stream);
   c->src.release(); c->tgt.release();
   c->table.release(); c->vox.release(); c->sums.release(); c->slot_of_point.release(); c->counters.release();
@@ -668,6 +691,7 @@ void rg_destroy(rg_ctx* c) {
   if (c->result_host) pool().pinned_free(c->result_host);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->ev_upload) cudaEventDestroy(c->ev_upload);
   if (c->own_stream && c->stream) pool().stream_put(c->device, c->stream);
   delete c;
 }
@@ -773,7 +797,13 @@ size_t rg_get_covariances(rg_ctx* c, int which, double* out) {
 
 int rg_calculate_covariances(rg_ctx* c, int which) {
   CHECK_CTX(c);
+  // inside a batch the estimation runs on the pair's own setup stream (the one its uploads use), so that the uploads and
+  // kNN kernels of different pairs overlap; the batch stream is ordered after it
+  cudaStream_t saved = c->stream;
+  const bool side = c->batch && c->upload_stream && c->upload_stream != c->stream;
+  if (side) { cudaEventRecord(c->ev_upload, c->stream); cudaStreamWaitEvent(c->upload_stream, c->ev_upload, 0); c->stream = c->upload_stream; }
   int rc = calc_cov(c, which == RG_SOURCE ? c->src : c->tgt);
+  if (side) { cudaEventRecord(c->ev_upload, c->stream); c->stream = saved; c->side_pending = true; }   // joined lazily (use_device) or by rg_batch_align
   if (rc == RG_OK && which == RG_TARGET) { c->voxel_ok = false; c->st_ok = false; }
   return rc;
 }
@@ -1001,6 +1031,7 @@ int rg_batch_create(int device, int n_pairs, rg_batch** out) {
     }
     b->setup_streams.push_back(st); b->setup_events.push_back(ev);
   }
+  for (int i = 0; i < n_pairs; i++) b->pairs[i]->upload_stream = b->setup_streams[i % n_setup];
   *out = b;
   return RG_OK;
 }

@@ -1,0 +1,64 @@
+// drop_in_sequence.cpp — compiles the product's C++ drop-in class (include/rot_gicp/gicp/rot_vgicp.hpp) and drives it
+// with the exact statement sequence of LidarOdometry::scanRegeistration (src/lidarOdometry.cpp:448-501 of the reference).
+// Built by tests/test_gpu_cpp_dropin.py against oracle/ref_shim (the image has no PCL/Eigen; a ROLO checkout would use its
+// own) and linked with librolo_gicp_b200.so. Prints the rotation estimate and the translation result.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include <pcl/common/transforms.h>
+#include <rot_gicp/gicp/rot_vgicp.hpp>
+
+using PointType = pcl::PointXYZI;
+
+static pcl::PointCloud<PointType>::Ptr read_cloud(const char* path) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) { std::perror(path); std::exit(2); }
+  std::fseek(f, 0, SEEK_END); long bytes = std::ftell(f); std::fseek(f, 0, SEEK_SET);
+  std::vector<float> buf(bytes / 4);
+  if (std::fread(buf.data(), 1, bytes, f) != (size_t)bytes) std::exit(2);
+  std::fclose(f);
+  pcl::PointCloud<PointType>::Ptr c(new pcl::PointCloud<PointType>);
+  c->resize(buf.size() / 4);
+  for (size_t i = 0; i < c->size(); i++) { c->points[i].x = buf[i * 4]; c->points[i].y = buf[i * 4 + 1]; c->points[i].z = buf[i * 4 + 2]; c->points[i].intensity = 1.f; }
+  return c;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 2;
+  pcl::PointCloud<PointType>::Ptr featureLast = read_cloud(argv[1]);
+  pcl::PointCloud<PointType>::Ptr featureOld = read_cloud(argv[2]);
+  Eigen::Affine3f transformation_interpolated = Eigen::Affine3f::Identity();
+  Eigen::Vector3d TranslationOld(0.01, 0.0, 0.0);
+  float CT_lambda = 0.3f;
+
+  // ---- lidarOdometry.cpp:453-500, statement for statement ----
+  pcl::PointCloud<PointType>::Ptr feature_propagated(new pcl::PointCloud<PointType>);
+  pcl::PointCloud<PointType>::Ptr aligned(new pcl::PointCloud<PointType>);
+  pcl::transformPointCloud(*featureOld, *feature_propagated, transformation_interpolated);
+  fast_gicp::RotVGICP<PointType, PointType> rot_vgicp;
+  rot_vgicp.setPolarResolution(0.175, 0.175, 2.0);
+  rot_vgicp.setNumThreads(8);
+  rot_vgicp.clearTarget();
+  rot_vgicp.clearSource();
+  rot_vgicp.setInputTarget(featureLast);
+  rot_vgicp.setInputSource(feature_propagated);
+  rot_vgicp.align(*aligned);
+  Eigen::Matrix4f trans = rot_vgicp.getFinalTransformation();
+  Eigen::Vector3d Translation(trans(0, 3), trans(1, 3), trans(2, 3));
+  aligned->clear();
+  Eigen::Vector3d Reg_translation = Eigen::Vector3d::Zero();
+  rot_vgicp.computeTranslation(*aligned, Reg_translation, Translation, TranslationOld, 0.1, 0.1, CT_lambda);
+  // -------------------------------------------------------------
+  std::printf("converged=%d R0=[% .6f % .6f % .6f] t=[% .6f % .6f % .6f] aligned=%zu first=[% .5f % .5f % .5f]\n", (int)rot_vgicp.hasConverged(),
+              trans(0, 0), trans(0, 1), trans(0, 2), Reg_translation(0), Reg_translation(1), Reg_translation(2), aligned->size(),
+              aligned->points[0].x, aligned->points[0].y, aligned->points[0].z);
+  // the aliasing check of rot_vgicp_impl.hpp:150-152 must throw std::invalid_argument
+  try { pcl::PointCloud<PointType>& alias = const_cast<pcl::PointCloud<PointType>&>(*feature_propagated); rot_vgicp.align(alias); std::printf("alias=NOTHROW\n"); }
+  catch (const std::invalid_argument&) { std::printf("alias=invalid_argument\n"); }
+  // evaluateCost + covariances round trip
+  Eigen::Matrix<double, 6, 6> H; Eigen::Matrix<double, 6, 1> b;
+  double c = rot_vgicp.evaluateCost(Eigen::Matrix4f::Identity(), &H, &b);
+  std::printf("cost=%.6f H00=%.6f covs=%zu\n", c, H(0, 0), rot_vgicp.getSourceCovariances().size());
+  return 0;
+}
