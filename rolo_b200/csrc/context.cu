@@ -242,7 +242,8 @@ struct rg_ctx {
   unsigned* flag_host = nullptr;        // mapped pinned
   double* result_view = nullptr;        // where the kernel writes this pair's result (own block or the batch's)
   unsigned* flag_view = nullptr;
-  int blocks_per_pair = 0;
+  int lin_grid = 0, lin_tiles = 0;      // persistent-CTA grid and tile count of the stand-alone launch
+  DevBuf<int> sched_dev;
   double R_lin[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
   bool have_corr = false;
   size_t num_corr = 0;
@@ -276,6 +277,7 @@ struct rg_batch {
   unsigned* flag_host = nullptr;        // mapped pinned [P]
   std::vector<int> active;
   DevBuf<LinStatic> st_sub; DevBuf<LinDyn> dyn_sub;
+  DevBuf<int> sched_dev; std::vector<int> sched_group; int sched_grid = 0, sched_tiles = 0;   // schedule of the last launched group
   std::vector<cudaStream_t> setup_streams;   // covariance / voxel-map stages of different pairs overlap on these
   std::vector<cudaEvent_t> setup_events;
   cudaEvent_t ev_inputs = nullptr;
@@ -459,14 +461,7 @@ int sm_count(int device) {
   return n;
 }
 
-int choose_blocks_per_pair(int device, int n, int n_pairs) {
-  const int ntiles = std::max(1, (n + TILE_PTS - 1) / TILE_PTS);
-  const int slots = sm_count(device) * 2;                     // 2 resident CTAs per SM (launch bounds)
-  static const int waves = [] { const char* e = getenv("ROLO_LIN_WAVES"); int w = e ? atoi(e) : 2; return (w >= 1 && w <= 16) ? w : 2; }();
-  int per_pair = std::max(1, (slots * waves) / n_pairs);             // whole waves of CTAs over the batch (never a ragged extra wave)
-  if (n_pairs == 1) per_pair = slots;
-  return std::min(ntiles, per_pair);
-}
+int lin_slots(int device) { return sm_count(device) * 2; }   // 2 resident CTAs per SM (launch bounds of the fused kernel)
 
 // make sure the static descriptor + scratch for the fused kernel exist
 int prepare_linearize(rg_ctx* c) {
@@ -480,10 +475,19 @@ int prepare_linearize(rg_ctx* c) {
   const int n_pairs = c->batch ? (int)c->batch->pairs.size() : 1;
   const int lo = (c->shard_hi > c->shard_lo) ? c->shard_lo : 0;
   const int n_eval = (c->shard_hi > c->shard_lo) ? (c->shard_hi - c->shard_lo) : c->src.n;
-  c->blocks_per_pair = choose_blocks_per_pair(c->device, n_eval, n_pairs);
+  (void)n_pairs;
+  {   // stand-alone launch shape: one pair, persistent CTAs
+    std::vector<int> sched;
+    const int ntiles = (n_eval + TILE_PTS - 1) / TILE_PTS;
+    c->lin_grid = std::max(1, std::min(ntiles, lin_slots(c->device)));
+    build_schedule(&n_eval, 1, c->lin_grid, sched, c->lin_tiles);
+    RG_CUDA(c, c->sched_dev.ensure(c->device, sched.size()));
+    RG_CUDA(c, cudaMemcpyAsync(c->sched_dev.p, sched.data(), sched.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
   RG_CUDA(c, c->corr.ensure(c->device, (size_t)n_eval * noff));
   c->corr_noff = noff; c->have_corr = false;
-  RG_CUDA(c, c->partials.ensure(c->device, (size_t)c->blocks_per_pair * RES_N));
+  RG_CUDA(c, c->partials.ensure(c->device, (size_t)lin_slots(c->device) * RES_N));   // any launch grid fits
   if (!c->counter.p) { RG_CUDA(c, c->counter.ensure(c->device, 4)); RG_CUDA(c, cudaMemsetAsync(c->counter.p, 0, 4 * sizeof(unsigned), c->stream)); }
   RG_CUDA(c, c->result_dev.ensure(c->device, RES_N));
   RG_CUDA(c, c->st_dev.ensure(c->device, 1));
@@ -587,8 +591,8 @@ int evaluate_single(rg_ctx* c, const host::Request& r, const double* g3, const d
   if (int rc = make_dyn(c, r, g3, l3, dtn, dtn1, d, mode, refresh)) return rc;
   d.seq = ++g_seq;
   LinLaunch L;
-  L.mode = mode; L.refresh = refresh; L.noff = c->corr_noff; L.n_pairs = 1; L.blocks_per_pair = c->blocks_per_pair;
-  L.st = c->st_dev.p; L.dyn = nullptr;
+  L.mode = mode; L.refresh = refresh; L.noff = c->corr_noff; L.ct = (r.kind == host::REQ_T3_LIN || r.kind == host::REQ_T_ERROR) ? 1 : 0; L.n_pairs = 1; L.grid = c->lin_grid; L.total_tiles = c->lin_tiles;
+  L.st = c->st_dev.p; L.dyn = nullptr; L.sched = c->sched_dev.p;
   if (c->profile) cudaEventRecord(c->ev0, c->stream);
   RG_CUDA(c, launch_linearize(L, &d, c->stream));
   g_launches++;
@@ -687,7 +691,7 @@ void rg_destroy(rg_ctx* c) {
   c->fe_counts.release(); c->fe_picked.release(); c->fe_label.release(); c->fe_corner_cnt.release(); c->fe_surf_cnt.release();
   c->fe_range_image.release(); c->fe_prange.release(); c->fe_curv.release(); c->fe_full.release(); c->fe_extracted.release();
   c->fe_corner_ring.release(); c->fe_surf_ring.release(); c->fe_corner_out.release(); c->fe_surf_out.release();
-  c->corr.release(); c->partials.release(); c->counter.release(); c->result_dev.release(); c->st_dev.release(); c->staging.release();
+  c->corr.release(); c->partials.release(); c->counter.release(); c->result_dev.release(); c->st_dev.release(); c->staging.release(); c->sched_dev.release();
   if (c->result_host) pool().pinned_free(c->result_host);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1041,7 +1045,7 @@ void rg_batch_destroy(rg_batch* b) {
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (size_t i = b->pairs.size(); i-- > 0;) rg_destroy(b->pairs[i]);   // pair 0 (stream owner) last
-  b->st_dev.release(); b->dyn_dev.release(); b->st_sub.release(); b->dyn_sub.release();
+  b->st_dev.release(); b->dyn_dev.release(); b->st_sub.release(); b->dyn_sub.release(); b->sched_dev.release();
   if (b->dyn_host) pool().pinned_free(b->dyn_host);
   if (b->result_host) pool().pinned_free(b->result_host);
   if (b->flag_host) pool().pinned_free(b->flag_host);
@@ -1067,7 +1071,7 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
   // stage 1+2: covariances and voxel maps of every pair. Pairs are spread over a few setup streams so that the
   // small, latency-bound kernels of one pair (radix-sort passes, bbox, Morton codes, voxel insert) overlap the
   // big kNN kernels of the others; the batch stream joins them before the lock-step iterations start.
-  int noff = -1, bpp = -1;
+  int noff = -1;
   const int S = (int)b->setup_streams.size();
   RG_CUDA(nullptr, cudaEventRecord(b->ev_inputs, b->stream));
   for (int si = 0; si < S; si++) RG_CUDA(nullptr, cudaStreamWaitEvent(b->setup_streams[si], b->ev_inputs, 0));
@@ -1088,14 +1092,14 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
   for (int i = 0; i < P; i++) {
     rg_ctx* c = b->pairs[i];
     if (int rc = prepare_linearize(c)) return rc;
-    if (noff < 0) { noff = c->corr_noff; bpp = c->blocks_per_pair; }
+    if (noff < 0) noff = c->corr_noff;
     if (c->corr_noff != noff) return set_err(c, RG_ERR_INVALID, "batch align: all pairs must use the same neighbor search method");
-    bpp = std::min(bpp, c->blocks_per_pair);
     double g[16];
     if (guesses) for (int k = 0; k < 16; k++) g[k] = (double)guesses[i * 16 + k]; else host::mat4_identity(g);
     c->lsq.begin_align(g);
   }
   b->lin_us_sum = 0; b->lin_launches = 0;
+  b->sched_group.clear();   // cloud sizes may have changed since the last call
   std::vector<host::Request> req(P);
   std::vector<int> group;
   std::vector<LinStatic> st_host(P);
@@ -1128,8 +1132,20 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
         st_arr = b->st_sub.p;
       }
       RG_CUDA(nullptr, cudaMemcpyAsync(b->dyn_dev.p, b->dyn_host, sizeof(LinDyn) * G, cudaMemcpyHostToDevice, b->stream));
+      if (b->sched_group != group) {   // (re)build the persistent-CTA schedule for this set of pairs
+        std::vector<int> npts(G), sched;
+        long long tiles = 0;
+        for (int gi = 0; gi < G; gi++) { npts[gi] = st_host[group[gi]].n; tiles += (npts[gi] + TILE_PTS - 1) / TILE_PTS; }
+        b->sched_grid = (int)std::max<long long>(1, std::min<long long>(tiles, lin_slots(b->device)));
+        build_schedule(npts.data(), G, b->sched_grid, sched, b->sched_tiles);
+        RG_CUDA(nullptr, b->sched_dev.ensure(b->device, (size_t)3 * P + 1));
+        RG_CUDA(nullptr, cudaMemcpyAsync(b->sched_dev.p, sched.data(), sched.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream));
+        RG_CUDA(nullptr, cudaStreamSynchronize(b->stream));
+        b->sched_group = group;
+      }
       LinLaunch L;
-      L.mode = mode; L.refresh = refresh; L.noff = noff; L.n_pairs = G; L.blocks_per_pair = bpp; L.st = st_arr; L.dyn = b->dyn_dev.p;
+      L.mode = mode; L.refresh = refresh; L.noff = noff; L.ct = 0; L.n_pairs = G; L.grid = b->sched_grid; L.total_tiles = b->sched_tiles;
+      L.st = st_arr; L.dyn = b->dyn_dev.p; L.sched = b->sched_dev.p;
       cudaEventRecord(b->ev0, b->stream);
       RG_CUDA(nullptr, launch_linearize(L, nullptr, b->stream));
       g_launches++;

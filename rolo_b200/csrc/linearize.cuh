@@ -1,6 +1,7 @@
 // linearize.cuh — launch interface of the fused correspondence + Mahalanobis + Jacobian + reduction kernel.
 #pragma once
 #include "common.cuh"
+#include <vector>
 
 namespace rolo {
 
@@ -15,7 +16,7 @@ struct LinStatic {
   const VoxSlot* table;
   const VoxPayload* vox;
   int* corr;                  // [n * noff] cached compact voxel id (-1 = none)
-  double* partials;           // [blocks_per_pair][RES_N]
+  double* partials;           // [CTAs touching this pair][RES_N] (capacity: the launch grid)
   unsigned* counter;          // ticket for the last-block reduction (zero before launch, self-resetting)
   double* result;             // [RES_N] (device memory, or mapped pinned host memory)
   unsigned* done_flag;        // optional mapped host flag: receives `seq` after result is visible
@@ -39,11 +40,17 @@ struct LinLaunch {
   int mode;                   // LinMode
   int refresh;                // 1: probe the voxel table and rewrite corr; 0: use cached corr
   int noff;                   // 1, 7 or 27
+  int ct;                     // 1: continuous-time term active (translation stage evaluations)
   int n_pairs;
-  int blocks_per_pair;
+  int grid;                   // persistent CTAs; CTA g owns tiles [g*T/G, (g+1)*T/G) of the batch's global tile sequence
+  int total_tiles;            // T
   const LinStatic* st;        // device array [n_pairs]
   const LinDyn* dyn;          // device array [n_pairs]
+  const int* sched;           // device int[3*n_pairs + 1] from build_schedule(): tile_prefix | cta_first | cta_count
 };
+
+// host: per-pair tile prefix and the range of CTAs that touch each pair, for `grid` persistent CTAs
+void build_schedule(const int* n_points, int n_pairs, int grid, std::vector<int>& sched, int& total_tiles);
 
 // dyn0: host copy of the pose block, passed by value as a kernel parameter when L.dyn == nullptr
 // (single-pair path: no H2D copy per evaluation). Ignored when L.dyn is a device array.
