@@ -207,7 +207,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--pairs", type=int, default=32, help="scan pairs per GPU per step")
+    ap.add_argument("--pairs", type=int, default=128, help="scan pairs per GPU per step (128 = BASELINE configs[2]: 1024 pairs over 8 GPUs)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

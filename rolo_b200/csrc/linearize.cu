@@ -186,6 +186,17 @@ linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict_
       const float af3 = cv[3 * TILE_PTS], af4 = cv[4 * TILE_PTS], af5 = cv[5 * TILE_PTS];
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[stage]);
+      // producer duty first, compute second: refill the stage that was consumed in the PREVIOUS iteration (every warp
+      // released it at the top of that iteration, so this wait is short) with the tile NSTAGES-1 ahead. Issuing it here
+      // instead of after this thread's own math keeps the ring full even though thread 0 also computes.
+      if (tid == 0 && it > 0) {
+        const int tl = t - 1 + NSTAGES;
+        if (tl < t1) {
+          const int ps = (it - 1) % NSTAGES;
+          mbar_wait(&s_empty[ps], (uint32_t)((it - 1) / NSTAGES) & 1u);
+          issue(tl, ps);
+        }
+      }
 
       const int i = lt * TILE_PTS + tid;
       if (i < n) {
@@ -330,14 +341,6 @@ linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict_
               acc[10] += hit ? 1.0 : 0.0;
             }
           }
-        }
-      }
-      // producer: refill this stage with the tile NSTAGES iterations ahead once every warp has released it
-      if (tid == 0) {
-        const int tl = t + NSTAGES;
-        if (tl < t1) {
-          mbar_wait(&s_empty[stage], phase);
-          issue(tl, stage);
         }
       }
     }
