@@ -23,7 +23,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
           "--expt-relaxed-constexpr", "-Xptxas", "-v", "-I", os.path.join(HERE, "..", "include")]
 EXTRA = os.environ.get("ROLO_NVCC_FLAGS", "").split()
-SOURCES = ["linearize.cu", "voxelmap.cu", "covariance.cu", "frontend.cu", "context.cu"]
+SOURCES = ["linearize.cu", "voxelmap.cu", "covariance.cu", "frontend.cu", "context.cu", "testing_hooks.cu"]
 
 
 def _deps():

@@ -1,0 +1,44 @@
+// testing_hooks.cu — exports host-side logic for the CPU-only tests (include/rolo_gicp_testing.h). No CUDA calls.
+#include "../../include/rolo_gicp_testing.h"
+#include "linearize.cuh"
+#include "lsq_host.hpp"
+
+using namespace rolo;
+
+struct rgt_lsq { host::LsqDriver d; };
+
+extern "C" {
+
+rgt_lsq* rgt_lsq_create(int optimizer, int max_iterations, double rotation_epsilon, double transformation_epsilon) {
+  rgt_lsq* p = new rgt_lsq;
+  p->d.cfg.optimizer = optimizer; p->d.cfg.max_iterations = max_iterations;
+  p->d.cfg.rotation_epsilon = rotation_epsilon; p->d.cfg.transformation_epsilon = transformation_epsilon;
+  return p;
+}
+void rgt_lsq_destroy(rgt_lsq* p) { delete p; }
+void rgt_lsq_begin_align(rgt_lsq* p, const double guess[16]) { p->d.begin_align(guess); }
+void rgt_lsq_begin_translation(rgt_lsq* p, const double trans[3]) { p->d.begin_translation(trans); }
+int rgt_lsq_want(rgt_lsq* p, double pose16[16], double t3[3]) {
+  host::Request r;
+  if (!p->d.want(r)) return RGT_REQ_NONE;
+  if (r.kind == host::REQ_T3_LIN || r.kind == host::REQ_T_ERROR) { for (int i = 0; i < 3; i++) t3[i] = r.t[i]; }
+  else { for (int i = 0; i < 16; i++) pose16[i] = r.pose[i]; }
+  return r.kind;
+}
+void rgt_lsq_feed(rgt_lsq* p, const double* H, const double* b, double cost) { p->d.feed(H, b, cost); }
+void rgt_lsq_state(const rgt_lsq* p, double pose16[16], double t3[3], int* nr_iterations, int* converged, int* failed, double final_hessian36[36]) {
+  for (int i = 0; i < 16; i++) pose16[i] = p->d.x0[i];
+  for (int i = 0; i < 3; i++) t3[i] = p->d.t0[i];
+  *nr_iterations = p->d.nr_iterations; *converged = p->d.converged ? 1 : 0; *failed = p->d.failed ? 1 : 0;
+  for (int i = 0; i < 36; i++) final_hessian36[i] = p->d.final_hessian[i];
+}
+int rgt_build_schedule(const int* n_points, int n_pairs, int grid, int* sched) {
+  std::vector<int> s; int total = 0;
+  build_schedule(n_points, n_pairs, grid, s, total);
+  for (size_t i = 0; i < s.size(); i++) sched[i] = s[i];
+  return total;
+}
+void rgt_se3_exp(const double a[6], double T[16]) { host::se3_exp_mat4(a, T); }
+void rgt_ldlt_solve(const double* A, const double* rhs, int n, double* x) { host::ldlt_solve(A, rhs, n, x); }
+
+}  // extern "C"
