@@ -126,3 +126,26 @@ def test_point_order_invariance(small_pair):
     g2.setSourceCovariances(cs); g2.setTargetCovariances(o.getTargetCovariances())
     c2, H2, b2 = g2.linearize(T_gt)
     assert rel_err(c2, c) <= 1e-11 and rel_err(H2, H) <= 1e-11
+
+
+def test_per_frame_object_lifecycle_is_leak_free(tiny_pair):
+    """lidarOdometry.cpp:460 constructs a fresh registration object every frame: device buffers must come back from the
+    process-global pool (no growth of device memory after warm-up) and results must not depend on the recycled buffers."""
+    import torch
+    tgt, src, _ = tiny_pair
+
+    def frame():
+        r = RotVGICP(); r.setPolarResolution(0.175, 0.175, 2.0); r.setNumThreads(0)
+        r.clearTarget(); r.clearSource(); r.setInputTarget(tgt); r.setInputSource(src)
+        T = r.align().copy()
+        t = r.computeTranslation(np.zeros(3), T[:3, 3].astype(np.float64), np.zeros(3), 0.1, 0.1, 0.3)
+        return T, t
+    T0, t0 = frame()
+    for _ in range(5):
+        frame()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(100):
+        T, t = frame()
+        assert np.array_equal(T, T0) and np.array_equal(t, t0)
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 8 * 1024 * 1024
