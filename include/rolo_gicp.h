@@ -177,6 +177,15 @@ int rg_set_reduce_hook(rg_ctx*, rg_reduce_fn fn, void* user, int on_device);
  * the FULL cloud (kNN neighbourhoods must not be cut at shard borders). lo must be a multiple of 256 (the TMA tile);
  * lo == hi == 0 restores the whole cloud. Reset by rg_set_input_source*. */
 int rg_set_source_shard(rg_ctx*, size_t lo, size_t hi);
+/* Fused reduction over NVLink peer memory (alternative to the reduce hook, one process per GPU on one node):
+ * every rank exports a CUDA-IPC handle of its exchange buffer (rg_shard_export, 64 bytes), the handles are all-gathered by the
+ * caller (MPI / torch.distributed / any transport), and rg_shard_connect maps the peers. From then on the LAST CTA of each
+ * linearize/compute_error launch stores this rank's 32 partial sums into every peer's buffer with P2P stores, waits for the
+ * peers' rows and adds them in rank order inside the same kernel: no NCCL call, no extra launch, no host copy; all ranks
+ * obtain bit-identical sums. Every rank must issue the same sequence of evaluations (they do: identical sums => identical
+ * optimiser decisions). world <= 8. A peer that never arrives is reported as RG_ERR_CUDA after a bounded wait. */
+int rg_shard_export(rg_ctx*, void* ipc_handle_64_bytes);
+int rg_shard_connect(rg_ctx*, int rank, int world, const void* ipc_handles /* world x 64 bytes */);
 
 /* ---- upstream range-image passes ------------------------------------------------------------------------ */
 /* ImageProjection::projectPointCloud + cloudExtraction (imageProjection.cpp:399-505), deskew disabled

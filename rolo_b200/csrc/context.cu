@@ -255,6 +255,11 @@ struct rg_ctx {
 
   rg_reduce_fn reduce_fn = nullptr; void* reduce_user = nullptr; int reduce_on_device = 0;
   int shard_lo = 0, shard_hi = 0;       // evaluation range within the source cloud (0,0 = all)
+  // fused NVLink reduction (rg_shard_connect)
+  double* xchg = nullptr;               // own exchange buffer (plain cudaMalloc: exported through CUDA IPC)
+  double* peer_xchg[XCHG_MAX_RANKS] = {nullptr};
+  int p2p_rank = 0, p2p_world = 0;
+  unsigned shard_seq = 0;
 
   // front end (range-image projection + feature extraction) scratch
   DevBuf<unsigned char> fe_raw;
@@ -509,6 +514,8 @@ int prepare_linearize(rg_ctx* c) {
   st.result = to_host || c->batch ? c->result_view : c->result_dev.p;
   st.done_flag = to_host || c->batch ? c->flag_view : nullptr;
   st.grid = make_grid(c);
+  st.shard_rank = c->p2p_rank; st.shard_world = (c->p2p_world > 1 && !c->batch) ? c->p2p_world : 0;
+  for (int p = 0; p < XCHG_MAX_RANKS; p++) st.peer_xchg[p] = c->peer_xchg[p];
   RG_CUDA(c, cudaMemcpyAsync(c->st_dev.p, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
   if (c->batch) RG_CUDA(c, cudaMemcpyAsync(c->batch->st_dev.p + c->batch_index, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
   RG_CUDA(c, cudaStreamSynchronize(c->stream));   // `st` is a stack object
@@ -519,7 +526,7 @@ int prepare_linearize(rg_ctx* c) {
 void fill_dyn_pose(LinDyn& d, const double* T, const double* Rm) {
   for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) d.R[i * 3 + j] = T[i * 4 + j]; d.t[i] = T[i * 4 + 3]; }
   for (int i = 0; i < 9; i++) d.Rm[i] = Rm[i];
-  d.ct[0] = d.ct[1] = d.ct[2] = 0.0; d.lam_c = 0.0; d.h_scale = 1.0; d.b_ct_scale = 0.0; d.pad = 0;
+  d.ct[0] = d.ct[1] = d.ct[2] = 0.0; d.lam_c = 0.0; d.h_scale = 1.0; d.b_ct_scale = 0.0; d.shard_seq = 0;
 }
 
 // Build the launch description of one evaluation request; returns mode/refresh.
@@ -590,6 +597,7 @@ int evaluate_single(rg_ctx* c, const host::Request& r, const double* g3, const d
   LinDyn d; int mode = 0, refresh = 0;
   if (int rc = make_dyn(c, r, g3, l3, dtn, dtn1, d, mode, refresh)) return rc;
   d.seq = ++g_seq;
+  d.shard_seq = (c->p2p_world > 1) ? ++c->shard_seq : 0u;
   LinLaunch L;
   L.mode = mode; L.refresh = refresh; L.noff = c->corr_noff; L.ct = (r.kind == host::REQ_T3_LIN || r.kind == host::REQ_T_ERROR) ? 1 : 0; L.n_pairs = 1; L.grid = c->lin_grid; L.total_tiles = c->lin_tiles;
   L.st = c->st_dev.p; L.dyn = nullptr; L.sched = c->sched_dev.p;
@@ -608,6 +616,7 @@ int evaluate_single(rg_ctx* c, const host::Request& r, const double* g3, const d
     if (c->reduce_fn) if (int rc = c->reduce_fn(c->reduce_user, res, RES_N, 0, nullptr)) return set_err(c, RG_ERR_CUDA, "reduce hook failed (" + std::to_string(rc) + ")");
   }
   if (c->profile) { cudaEventSynchronize(c->ev1); float ms = 0; cudaEventElapsedTime(&ms, c->ev0, c->ev1); c->last_kernel_us = ms * 1e3; }
+  if (c->p2p_world > 1 && res[28] != res[28]) return set_err(c, RG_ERR_CUDA, "sharded registration: a peer rank never delivered its partial sums (bounded wait expired)");
   if (refresh) { c->have_corr = true; c->num_corr = (size_t)(res[28] + 0.5); }
   return RG_OK;
 }
@@ -692,6 +701,8 @@ void rg_destroy(rg_ctx* c) {
   c->fe_range_image.release(); c->fe_prange.release(); c->fe_curv.release(); c->fe_full.release(); c->fe_extracted.release();
   c->fe_corner_ring.release(); c->fe_surf_ring.release(); c->fe_corner_out.release(); c->fe_surf_out.release();
   c->corr.release(); c->partials.release(); c->counter.release(); c->result_dev.release(); c->st_dev.release(); c->staging.release(); c->sched_dev.release();
+  for (int p = 0; p < XCHG_MAX_RANKS; p++) if (c->peer_xchg[p] && c->peer_xchg[p] != c->xchg) cudaIpcCloseMemHandle(c->peer_xchg[p]);
+  if (c->xchg) cudaFree(c->xchg);
   if (c->result_host) pool().pinned_free(c->result_host);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -989,6 +1000,41 @@ int rg_set_source_shard(rg_ctx* c, size_t lo, size_t hi) {
   if (lo == 0 && hi == 0) { c->shard_lo = c->shard_hi = 0; c->st_ok = false; c->have_corr = false; return RG_OK; }
   if (lo % TILE_PTS != 0 || hi <= lo || hi > (size_t)c->src.n) return set_err(c, RG_ERR_INVALID, "rg_set_source_shard: need lo % 256 == 0 and lo < hi <= source size");
   c->shard_lo = (int)lo; c->shard_hi = (int)hi; c->st_ok = false; c->have_corr = false;
+  return RG_OK;
+}
+
+int rg_shard_export(rg_ctx* c, void* handle) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (!handle) return set_err(c, RG_ERR_INVALID, "rg_shard_export: null handle");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!c->xchg) {
+    RG_CUDA(c, cudaMalloc((void**)&c->xchg, XCHG_DOUBLES * sizeof(double)));
+    RG_CUDA(c, cudaMemset(c->xchg, 0, XCHG_DOUBLES * sizeof(double)));
+  }
+  cudaIpcMemHandle_t h;
+  RG_CUDA(c, cudaIpcGetMemHandle(&h, c->xchg));
+  std::memcpy(handle, &h, sizeof(h));
+  return RG_OK;
+}
+
+int rg_shard_connect(rg_ctx* c, int rank, int world, const void* handles) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (world < 1 || world > XCHG_MAX_RANKS || rank < 0 || rank >= world || !handles || !c->xchg)
+    return set_err(c, RG_ERR_INVALID, "rg_shard_connect: bad arguments (call rg_shard_export first; world <= 8)");
+  for (int p = 0; p < world; p++) {
+    if (p == rank) { c->peer_xchg[p] = c->xchg; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const char*)handles + (size_t)p * 64, sizeof(h));
+    void* ptr = nullptr;
+    RG_CUDA(c, cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_xchg[p] = (double*)ptr;
+  }
+  RG_CUDA(c, cudaMemset(c->xchg, 0, XCHG_DOUBLES * sizeof(double)));
+  RG_CUDA(c, cudaDeviceSynchronize());
+  c->p2p_rank = rank; c->p2p_world = world; c->shard_seq = 0; c->st_ok = false;
+  c->reduce_fn = nullptr;
   return RG_OK;
 }
 

@@ -21,7 +21,16 @@ struct LinStatic {
   double* result;             // [RES_N] (device memory, or mapped pinned host memory)
   unsigned* done_flag;        // optional mapped host flag: receives `seq` after result is visible
   GridParams grid;
+  // point-sharded registration fused with its reduction over NVLink peer memory (optional, shard_world <= 1: off).
+  // peer_xchg[p] is rank p's exchange buffer (CUDA-IPC mapped): [2 parities][XCHG_MAX_RANKS source ranks][XCHG_STRIDE doubles];
+  // the last CTA stores this rank's 32 sums + a sequence word into every peer's buffer, waits for every peer's row in its
+  // own buffer and adds the rows in rank order: all ranks obtain bit-identical totals without an NCCL call or a host copy.
+  int shard_rank, shard_world;
+  double* peer_xchg[8];
 };
+constexpr int XCHG_MAX_RANKS = 8;
+constexpr int XCHG_STRIDE = 40;      // 32 values, 1 sequence word, pad (320 B rows)
+constexpr size_t XCHG_DOUBLES = (size_t)2 * XCHG_MAX_RANKS * XCHG_STRIDE;
 
 // Dynamic (per evaluation) part: poses and continuous-time terms.
 struct LinDyn {
@@ -33,7 +42,7 @@ struct LinDyn {
   double h_scale;             // 1 + lam_c / dtn^2
   double b_ct_scale;          // lam_c / dtn
   unsigned seq;               // value written to done_flag
-  unsigned pad;
+  unsigned shard_seq;         // evaluation counter of a sharded registration (identical on every rank)
 };
 
 struct LinLaunch {

@@ -58,8 +58,20 @@ def make_reduce_hook(group=None):
     return hook
 
 
-def sharded_registration(target, source, rank: int, world: int, device: int = -1, on_device: bool = True, group=None):
-    """A RotVGICP whose source is this rank's shard and whose evaluations are all-reduced across `world` ranks."""
+def connect_peers(reg, rank: int, world: int, group=None):
+    """Fused NVLink reduction: all-gather the CUDA-IPC handles of the ranks' exchange buffers and map them (one node)."""
+    import torch.distributed as dist
+    mine = reg.shardExport()
+    handles = [None] * world
+    dist.all_gather_object(handles, mine, group=group)
+    reg.shardConnect(rank, world, handles)
+    dist.barrier(group=group)     # nobody writes into a buffer that its owner has not zeroed yet
+
+
+def sharded_registration(target, source, rank: int, world: int, device: int = -1, on_device: bool = True, group=None, transport: str = "nccl"):
+    """A RotVGICP whose source is this rank's shard and whose evaluations are summed across `world` ranks, either by an
+    all-reduce hook (transport="nccl": NCCL on device buffers / gloo on host buffers) or inside the fused kernel itself
+    over NVLink peer memory (transport="p2p")."""
     from .registration import RotVGICP
     r = RotVGICP(device=device)
     r.setInputTarget(target)
@@ -69,5 +81,8 @@ def sharded_registration(target, source, rank: int, world: int, device: int = -1
         if hi <= lo:
             raise ValueError("source cloud too small for this many ranks")
         r.setSourceShard(lo, hi)
-        r.setReduceHook(make_reduce_hook(group), on_device)
+        if transport == "p2p":
+            connect_peers(r, rank, world, group)
+        else:
+            r.setReduceHook(make_reduce_hook(group), on_device)
     return r

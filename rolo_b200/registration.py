@@ -244,6 +244,16 @@ class RotVGICP:
 
     def setSourceShard(self, lo: int, hi: int): self._ck(self._L.rg_set_source_shard(self._h, lo, hi))
 
+    def shardExport(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self._L.rg_shard_export(self._h, buf))
+        return buf.raw
+
+    def shardConnect(self, rank: int, world: int, handles: list):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        self._ck(self._L.rg_shard_connect(self._h, rank, world, blob))
+
     def setReduceHook(self, fn, on_device: bool):
         """Sharded registration (config 4): fn(buf_ptr:int, count:int, on_device:bool, stream:int) -> int."""
         if fn is None:

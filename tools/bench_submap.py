@@ -15,8 +15,9 @@ rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 
 torch.cuda.set_device(local); dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-n_scans = int(sys.argv[1]) if len(sys.argv) > 1 else 77
-iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+_pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+n_scans = int(_pos[0]) if len(_pos) > 0 else 77
+iters = int(_pos[1]) if len(_pos) > 1 else 20
 sensor = "os1-128x1024"
 # 77 overlapping scans give ~1 cm point spacing: with the per-scan 2 cm range noise the 20-NN patches of the merged map
 # would be thinner than the noise (meaningless normals, for the reference as well), so the map scans use 4 mm noise
@@ -48,7 +49,11 @@ r.setInputTarget(target); r.setInputSource(source)
 if world > 1:
     lo, hi = shard_bounds(source.shape[0], rank, world, align=TILE)
     r.setSourceShard(lo, hi)
-    r.setReduceHook(make_reduce_hook(), True)
+    if "--p2p" in sys.argv:
+        from rolo_b200.dist import connect_peers
+        connect_peers(r, rank, world)          # reduction fused into the kernel over NVLink peer memory
+    else:
+        r.setReduceHook(make_reduce_hook(), True)
 r.calculate_covariances(capi.SOURCE); r.calculate_covariances(capi.TARGET); r.create_voxelmap()
 torch.cuda.synchronize()
 t_setup = time.perf_counter() - t0
@@ -65,7 +70,7 @@ if world > 1:
     tl = torch.tensor([t_lin, t_setup], dtype=torch.float64, device=dev); dist.all_reduce(tl, op=dist.ReduceOp.MAX); t_lin, t_setup = [float(x) for x in tl]
 if rank == 0:
     print(json.dumps({"config": f"scan-to-submap: {source.shape[0]} source pts (sharded x{world}) vs {target.shape[0]} target pts, UNIFORM 1.0 DIRECT7, GN x{iters}",
-                      "n_gpus": world, "voxels": int(r._L.rg_voxel_count(r._h)), "correspondences_shard0": int(r.numCorrespondences()),
+                      "n_gpus": world, "transport": ("p2p-fused" if "--p2p" in sys.argv else "nccl") if world > 1 else "none", "voxels": int(r._L.rg_voxel_count(r._h)), "correspondences_shard0": int(r.numCorrespondences()),
                       "setup_ms_cov_and_voxelmap": 1e3 * t_setup, "gn_iter_us_wall": 1e6 * t_lin, "gn_iters_per_s": 1.0 / t_lin,
                       "fused_kernel_us": kern_us / reps, "align_ms_incl_voxel_rebuild": 1e3 * t_align,
                       "pose_err_rad": erot, "pose_err_m": etr}))

@@ -28,8 +28,8 @@ def configure(r):
 
 
 ok = True
-for on_device in (True, False):
-    r = sharded_registration(tgt, src, rank, world, device=local, on_device=on_device, group=None if on_device else gloo)
+for on_device, transport in ((True, "p2p"), (True, "nccl"), (False, "nccl")):
+    r = sharded_registration(tgt, src, rank, world, device=local, on_device=on_device, group=None if on_device else gloo, transport=transport)
     configure(r)
     t0 = time.perf_counter(); T = r.align(); dt = time.perf_counter() - t0
     Td = r.getFinalPoseDouble()
@@ -44,7 +44,7 @@ for on_device in (True, False):
     good = drot <= 1e-9 and dtr <= 1e-9 and same_iters and spread == 0.0
     ok = ok and good
     if rank == 0:
-        print(f"on_device={on_device}: world={world} pose vs single-GPU {drot:.2e} rad {dtr:.2e} m, iters {r.nrIterations()} vs {ref.nrIterations()}, "
+        print(f"transport={transport} on_device={on_device}: world={world} pose vs single-GPU {drot:.2e} rad {dtr:.2e} m, iters {r.nrIterations()} vs {ref.nrIterations()}, "
               f"rank spread {spread:.1e}, align {1e3*dt:.2f} ms -> {'OK' if good else 'FAIL'}")
 dist.barrier()
 dist.destroy_process_group()
