@@ -221,6 +221,29 @@ int rg_feature_extraction(rg_ctx*, const float* extracted_xyzi, const int32_t* p
 int rg_front_end_frame(rg_ctx*, const void* host_raw_points, size_t n_points, const rg_projection_params* pp,
                        const rg_feature_params* fp, int which, int32_t* n_corner, int32_t* n_surface);
 
+/* ---- rolo/CloudInfoStamp at the ROS edge (msg/CloudInfoStamp.msg:1-28) ------------------------------
+ * The stages hand their products over on the device (rg_front_end_frame); these two calls produce / consume the ROS1
+ * wire image (roscpp serialisation, every cloud as pcl::toROSMsg writes a PointCloud<PointXYZI>: point_step 32) only
+ * where a ROS publisher / subscriber needs it.
+ *   stage 0 = the message imageProjection publishes (imageProjection.cpp:507-512): index arrays + cloud_projected;
+ *   stage 1 = the message featureExtraction publishes (featureExtraction.cpp:268-287): index arrays cleared,
+ *             cloud_projected kept, extracted_corner / extracted_surface filled, extracted_normal an empty cloud.
+ * The point records are packed on the device and copied straight into `out` (pinned memory: no staging copy).
+ * out == NULL: only *written (the size) is computed. */
+typedef struct rg_msg_header { uint32_t seq, stamp_sec, stamp_nsec; const char* frame_id; } rg_msg_header;
+typedef struct rg_cloud_info_scalars {
+  float start_orientation, end_orientation, orientation_diff;
+  float initial_guess[6];              /* X Y Z Roll Pitch Yaw */
+  const float* covariance; uint32_t n_covariance;
+  uint8_t odom_available;
+} rg_cloud_info_scalars;
+int rg_cloud_info_serialize(rg_ctx*, int stage, const rg_msg_header* hdr, const rg_cloud_info_scalars* scalars /* NULL: zeros */,
+                            uint8_t* out, size_t capacity, size_t* written);
+/* Consumer edge (lidarOdometry.cpp:521-524: fromROSMsg(extracted_corner), fromROSMsg(extracted_surface),
+ * featureLast = corner + surf): parses a serialised CloudInfoStamp and installs corner + surface as this context's
+ * source or target cloud; the point records are unpacked on the device. */
+int rg_set_input_from_cloud_info(rg_ctx*, int which, const uint8_t* msg, size_t len, int32_t* n_corner, int32_t* n_surface);
+
 #ifdef __cplusplus
 }
 #endif

@@ -262,6 +262,41 @@ def feature_extraction(proj: dict, n_scan, horizon, edge_threshold=0.8, surf_thr
     return {"curvature": curv, "neighbor_picked": picked, "label": label, "corner": corner[:nc.value].copy(), "surface": surf[:ns.value].copy()}
 
 
+def cloud_info_serialize(stage: int, seq: int, sec: int, nsec: int, frame: str, proj: dict, feat: dict | None = None,
+                         scalars9=None, covariance=None, odom_available: bool = False) -> bytes:
+    """ROS1 wire image of rolo/CloudInfoStamp as imageProjection (stage 0) / featureExtraction (stage 1) publish it
+    (cloud_info_oracle.cpp). `proj` / `feat` are image_projection() / feature_extraction() results."""
+    L = lib()
+    L.ro_cloud_info_serialize.restype = C.c_size_t
+    f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    vp = lambda a: C.c_void_p(a.ctypes.data) if a is not None and a.size else C.c_void_p(0)
+    st, en, col, rng, ext = i32(proj["start_ring_index"]), i32(proj["end_ring_index"]), i32(proj["point_col_ind"]), f32(proj["point_range"]), f32(proj["extracted"])
+    corner = f32(feat["corner"]) if feat is not None else np.zeros((0, 4), np.float32)
+    surf = f32(feat["surface"]) if feat is not None else np.zeros((0, 4), np.float32)
+    sc = f32(scalars9) if scalars9 is not None else np.zeros(9, np.float32)
+    cov = f32(covariance) if covariance is not None else np.zeros(0, np.float32)
+    args = lambda out, cap: (C.c_int(stage), C.c_uint32(seq), C.c_uint32(sec), C.c_uint32(nsec), C.c_char_p(frame.encode()), vp(st), vp(en), C.c_int(st.shape[0]),
+                             vp(col), vp(rng), vp(ext), C.c_int(ext.shape[0]), vp(corner), C.c_int(corner.shape[0]), vp(surf), C.c_int(surf.shape[0]),
+                             vp(sc), vp(cov), C.c_int(cov.shape[0]), C.c_int(1 if odom_available else 0), out, C.c_size_t(cap))
+    size = L.ro_cloud_info_serialize(*args(C.c_void_p(0), 0))
+    buf = np.empty(size, dtype=np.uint8)
+    L.ro_cloud_info_serialize(*args(C.c_void_p(buf.ctypes.data), size))
+    return buf.tobytes()
+
+
+def cloud_info_features(msg: bytes) -> tuple[np.ndarray, int, int]:
+    """lidarOdometry.cpp:521-524: featureLast = fromROSMsg(extracted_corner) + fromROSMsg(extracted_surface), (n, 4) xyzi."""
+    L = lib()
+    a = np.frombuffer(msg, dtype=np.uint8)
+    nc, ns = C.c_int(), C.c_int()
+    if L.ro_cloud_info_features(C.c_void_p(a.ctypes.data), C.c_size_t(a.size), C.c_void_p(0), C.byref(nc), C.byref(ns)) != 0:
+        raise ValueError("malformed CloudInfoStamp")
+    out = np.empty((nc.value + ns.value, 4), dtype=np.float32)
+    L.ro_cloud_info_features(C.c_void_p(a.ctypes.data), C.c_size_t(a.size), C.c_void_p(out.ctypes.data), C.byref(nc), C.byref(ns))
+    return out, nc.value, ns.value
+
+
 # ---- oracle/_ref: the REFERENCE's own rot_gicp sources compiled against oracle/ref_shim (see oracle/Makefile) ----
 _REF_PATH = os.path.join(_HERE, "_ref", "librolo_ref.so")
 _ref = None

@@ -39,6 +39,15 @@ class FeatureParams(C.Structure):
                 ("edge_threshold", C.c_float), ("surf_threshold", C.c_float), ("surf_leaf_size", C.c_float)]
 
 
+class MsgHeader(C.Structure):
+    _fields_ = [("seq", C.c_uint32), ("stamp_sec", C.c_uint32), ("stamp_nsec", C.c_uint32), ("frame_id", C.c_char_p)]
+
+
+class CloudInfoScalars(C.Structure):
+    _fields_ = [("start_orientation", C.c_float), ("end_orientation", C.c_float), ("orientation_diff", C.c_float), ("initial_guess", C.c_float * 6),
+                ("covariance", C.POINTER(C.c_float)), ("n_covariance", C.c_uint32), ("odom_available", C.c_uint8)]
+
+
 REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p)
 
 
@@ -100,7 +109,7 @@ def load():
         "rg_knn": [vp, i, i, ip], "rg_last_kernel_us": [vp],
         "rg_batch_create": [i, i, C.POINTER(vp)], "rg_batch_destroy": [vp], "rg_batch_ctx": [vp, i],
         "rg_batch_align": [vp, fp, fp], "rg_batch_last_linearize_us": [vp], "rg_batch_last_linearize_launches": [vp],
-        "rg_set_reduce_hook": [vp, REDUCE_FN, vp, i], "rg_set_source_shard": [vp, sz, sz], "rg_front_end_frame": [vp, vp, sz, vp, vp, i, vp, vp], "rg_shard_export": [vp, vp], "rg_shard_connect": [vp, i, i, vp], "rg_batch_stream": [vp], "rg_stream": [vp], "rg_kernel_launch_count": [],
+        "rg_set_reduce_hook": [vp, REDUCE_FN, vp, i], "rg_set_source_shard": [vp, sz, sz], "rg_front_end_frame": [vp, vp, sz, vp, vp, i, vp, vp], "rg_cloud_info_serialize": [vp, i, vp, vp, vp, sz, vp], "rg_set_input_from_cloud_info": [vp, i, vp, sz, vp, vp], "rg_shard_export": [vp, vp], "rg_shard_connect": [vp, i, i, vp], "rg_batch_stream": [vp], "rg_stream": [vp], "rg_kernel_launch_count": [],
     }
     for name, args in protos.items():
         getattr(L, name).argtypes = args

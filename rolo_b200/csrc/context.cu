@@ -20,6 +20,7 @@
 #include "frontend.cuh"
 #include "linearize.cuh"
 #include "lsq_host.hpp"
+#include "cloud_info.hpp"
 #include "voxelmap.cuh"
 
 using namespace rolo;
@@ -266,6 +267,9 @@ struct rg_ctx {
   DevBuf<int> fe_owner, fe_row_count, fe_col, fe_start, fe_end, fe_counts, fe_picked, fe_label, fe_corner_cnt, fe_surf_cnt;
   DevBuf<float> fe_range_image, fe_prange, fe_curv;
   DevBuf<float4> fe_full, fe_extracted, fe_corner_ring, fe_surf_ring, fe_corner_out, fe_surf_out;
+  DevBuf<unsigned char> fe_wire;        // packed PointXYZI records / uploaded message sections (cloud_info.hpp)
+  bool fe_frame_ok = false;             // rg_front_end_frame products are resident
+  int fe_n_scan = 0, fe_n[3] = {0, 0, 0};   // extracted, corner, surface counts of that frame
 
   rg_batch* batch = nullptr;            // non-null when owned by a batch
   int batch_index = 0;
@@ -699,7 +703,7 @@ void rg_destroy(rg_ctx* c) {
   c->fe_raw.release(); c->fe_owner.release(); c->fe_row_count.release(); c->fe_col.release(); c->fe_start.release(); c->fe_end.release();
   c->fe_counts.release(); c->fe_picked.release(); c->fe_label.release(); c->fe_corner_cnt.release(); c->fe_surf_cnt.release();
   c->fe_range_image.release(); c->fe_prange.release(); c->fe_curv.release(); c->fe_full.release(); c->fe_extracted.release();
-  c->fe_corner_ring.release(); c->fe_surf_ring.release(); c->fe_corner_out.release(); c->fe_surf_out.release();
+  c->fe_corner_ring.release(); c->fe_surf_ring.release(); c->fe_corner_out.release(); c->fe_surf_out.release(); c->fe_wire.release();
   c->corr.release(); c->partials.release(); c->counter.release(); c->result_dev.release(); c->st_dev.release(); c->staging.release(); c->sched_dev.release();
   for (int p = 0; p < XCHG_MAX_RANKS; p++) if (c->peer_xchg[p] && c->peer_xchg[p] != c->xchg) cudaIpcCloseMemHandle(c->peer_xchg[p]);
   if (c->xchg) cudaFree(c->xchg);
@@ -1376,6 +1380,7 @@ extern "C" int rg_front_end_frame(rg_ctx* c, const void* raw, size_t n_points, c
   if (h[3] != 0) return set_err(c, RG_ERR_UNSUPPORTED, "rg_front_end_frame: sector/ring capacity exceeded");
   if (n_corner) *n_corner = h[1];
   if (n_surface) *n_surface = h[2];
+  c->fe_frame_ok = true; c->fe_n_scan = pp->n_scan; c->fe_n[0] = h[0]; c->fe_n[1] = h[1]; c->fe_n[2] = h[2];
   Cloud& cl = which == RG_SOURCE ? c->src : c->tgt;
   const int n = h[1] + h[2];
   const int n_pad = (n + TILE_PTS - 1) / TILE_PTS * TILE_PTS;
@@ -1387,6 +1392,122 @@ extern "C" int rg_front_end_frame(rg_ctx* c, const void* raw, size_t n_points, c
     concat_clouds_kernel<<<(n_pad + 255) / 256, 256, 0, c->stream>>>(c->fe_corner_out.p, h[1], c->fe_surf_out.p, h[2], n_pad, cl.pts.p);
     RG_CUDA(c, cudaGetLastError());
   }
+  if (which == RG_TARGET) c->voxel_ok = false;
+  c->st_ok = false; c->have_corr = false;
+  if (which == RG_SOURCE) c->shard_lo = c->shard_hi = 0;
+  return RG_OK;
+}
+
+// ---- rolo/CloudInfoStamp wire image at the ROS edge (cloud_info.hpp) ------------------------------------------------
+
+// float4 (x, y, z, intensity) -> 32-byte pcl::PointXYZI record (x y z 1 | intensity 0 0 0)
+__global__ void pack_xyzi_kernel(const float4* __restrict__ in, int n, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = in[i];
+  out[2 * i] = make_float4(p.x, p.y, p.z, 1.f);
+  out[2 * i + 1] = make_float4(p.w, 0.f, 0.f, 0.f);
+}
+
+struct WireCloud { const unsigned char* data; int n, step, ox, oy, oz; };
+
+// corner + surface point records of a serialised message -> the context's float4 cloud (featureLast = corner + surf)
+__global__ void unpack_features_kernel(WireCloud a, WireCloud b, int n_pad, float4* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad) return;
+  float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
+  const WireCloud* w = nullptr; int j = 0;
+  if (i < a.n) { w = &a; j = i; } else if (i < a.n + b.n) { w = &b; j = i - a.n; }
+  if (w) {
+    const unsigned char* r = w->data + (size_t)j * w->step;
+    p.x = *reinterpret_cast<const float*>(r + w->ox); p.y = *reinterpret_cast<const float*>(r + w->oy); p.z = *reinterpret_cast<const float*>(r + w->oz);
+  }
+  out[i] = p;
+}
+
+extern "C" int rg_cloud_info_serialize(rg_ctx* c, int stage, const rg_msg_header* hdr, const rg_cloud_info_scalars* sc, uint8_t* out, size_t capacity,
+                                       size_t* written) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (!hdr || !written || (stage != 0 && stage != 1)) return set_err(c, RG_ERR_INVALID, "rg_cloud_info_serialize: bad arguments");
+  if (!c->fe_frame_ok) return set_err(c, RG_ERR_INVALID, "rg_cloud_info_serialize: no front-end frame resident (call rg_front_end_frame first)");
+  static const float no_cov[1] = {0.f};
+  wire::Scalars s{};
+  if (sc) {
+    s.startOrientation = sc->start_orientation; s.endOrientation = sc->end_orientation; s.orientationDiff = sc->orientation_diff;
+    for (int i = 0; i < 6; i++) s.initialGuess[i] = sc->initial_guess[i];
+    s.covariance = sc->n_covariance ? sc->covariance : no_cov; s.n_covariance = sc->n_covariance; s.odomAvailable = sc->odom_available;
+    if (sc->n_covariance && !sc->covariance) return set_err(c, RG_ERR_INVALID, "rg_cloud_info_serialize: null covariance");
+  } else { s.covariance = no_cov; }
+  const char* frame = hdr->frame_id ? hdr->frame_id : "";
+  const wire::Header h{hdr->seq, hdr->stamp_sec, hdr->stamp_nsec, frame, std::strlen(frame)};
+  wire::Sections sec;
+  wire::Writer w(out, capacity);
+  const size_t total = wire::write_cloud_info(w, stage, h, s, (uint32_t)c->fe_n_scan, (uint32_t)c->fe_n[0], (uint32_t)c->fe_n[1], (uint32_t)c->fe_n[2], sec);
+  *written = total;
+  if (!out) return RG_OK;
+  if (w.overflow) return set_err(c, RG_ERR_INVALID, "rg_cloud_info_serialize: output buffer too small");
+  const int n0 = c->fe_n[0], n1 = stage == 1 ? c->fe_n[1] : 0, n2 = stage == 1 ? c->fe_n[2] : 0;
+  const size_t recs = (size_t)n0 + n1 + n2;
+  RG_CUDA(c, c->fe_wire.ensure(c->device, std::max<size_t>(recs * wire::POINT_STEP, 32)));
+  float4* stage_buf = reinterpret_cast<float4*>(c->fe_wire.p);
+  const struct { const float4* src; int n; size_t off; } part[3] = {{c->fe_extracted.p, n0, sec.projected}, {c->fe_corner_out.p, n1, sec.corner}, {c->fe_surf_out.p, n2, sec.surface}};
+  size_t rec0 = 0;
+  for (int k = 0; k < 3; k++) {
+    if (part[k].n <= 0) continue;
+    g_launches++;
+    pack_xyzi_kernel<<<(part[k].n + 255) / 256, 256, 0, c->stream>>>(part[k].src, part[k].n, stage_buf + 2 * rec0);
+    RG_CUDA(c, cudaGetLastError());
+    RG_CUDA(c, cudaMemcpyAsync(out + part[k].off, stage_buf + 2 * rec0, (size_t)part[k].n * wire::POINT_STEP, cudaMemcpyDeviceToHost, c->stream));
+    rec0 += part[k].n;
+  }
+  if (stage == 0) {
+    RG_CUDA(c, cudaMemcpyAsync(out + sec.start_ring, c->fe_start.p, 4ull * c->fe_n_scan, cudaMemcpyDeviceToHost, c->stream));
+    RG_CUDA(c, cudaMemcpyAsync(out + sec.end_ring, c->fe_end.p, 4ull * c->fe_n_scan, cudaMemcpyDeviceToHost, c->stream));
+    if (n0 > 0) {
+      RG_CUDA(c, cudaMemcpyAsync(out + sec.col_ind, c->fe_col.p, 4ull * n0, cudaMemcpyDeviceToHost, c->stream));
+      RG_CUDA(c, cudaMemcpyAsync(out + sec.point_range, c->fe_prange.p, 4ull * n0, cudaMemcpyDeviceToHost, c->stream));
+    }
+  }
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RG_OK;
+}
+
+extern "C" int rg_set_input_from_cloud_info(rg_ctx* c, int which, const uint8_t* msg, size_t len, int32_t* n_corner, int32_t* n_surface) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (!msg || (which != RG_SOURCE && which != RG_TARGET)) return set_err(c, RG_ERR_INVALID, "rg_set_input_from_cloud_info: bad arguments");
+  wire::Parsed P;
+  if (!wire::parse_cloud_info(msg, len, P)) return set_err(c, RG_ERR_INVALID, "rg_set_input_from_cloud_info: malformed CloudInfoStamp message");
+  const wire::CloudView* cv[2] = {&P.corner, &P.surface};
+  for (int k = 0; k < 2; k++) {
+    const wire::CloudView& v = *cv[k];
+    if (v.n_points == 0) continue;
+    if (v.off_x < 0 || v.off_y < 0 || v.off_z < 0 || (v.off_x | v.off_y | v.off_z | (int)v.point_step) % 4 != 0 ||
+        (uint32_t)std::max(v.off_x, std::max(v.off_y, v.off_z)) + 4 > v.point_step)
+      return set_err(c, RG_ERR_UNSUPPORTED, "rg_set_input_from_cloud_info: feature clouds need 4-byte aligned float32 x/y/z fields");
+  }
+  const size_t bytes_a = (size_t)P.corner.n_points * P.corner.point_step, bytes_b = (size_t)P.surface.n_points * P.surface.point_step;
+  const size_t off_b = (bytes_a + 15) / 16 * 16;
+  RG_CUDA(c, c->fe_wire.ensure(c->device, std::max<size_t>(off_b + bytes_b, 32)));
+  if (bytes_a) RG_CUDA(c, cudaMemcpyAsync(c->fe_wire.p, msg + P.corner.data, bytes_a, cudaMemcpyHostToDevice, c->stream));
+  if (bytes_b) RG_CUDA(c, cudaMemcpyAsync(c->fe_wire.p + off_b, msg + P.surface.data, bytes_b, cudaMemcpyHostToDevice, c->stream));
+  Cloud& cl = which == RG_SOURCE ? c->src : c->tgt;
+  const int n = (int)(P.corner.n_points + P.surface.n_points);
+  const int n_pad = (n + TILE_PTS - 1) / TILE_PTS * TILE_PTS;
+  RG_CUDA(c, cl.pts.ensure(c->device, std::max(n_pad, TILE_PTS)));
+  RG_CUDA(c, cl.cov6.ensure(c->device, (size_t)std::max(n_pad, TILE_PTS) * COV_PLANES));
+  cl.n = n; cl.n_pad = n_pad; cl.has_cov = false; cl.host_identity = nullptr;
+  if (n > 0) {
+    const WireCloud a{c->fe_wire.p, (int)P.corner.n_points, (int)P.corner.point_step, P.corner.off_x, P.corner.off_y, P.corner.off_z};
+    const WireCloud b{c->fe_wire.p + off_b, (int)P.surface.n_points, (int)P.surface.point_step, P.surface.off_x, P.surface.off_y, P.surface.off_z};
+    g_launches++;
+    unpack_features_kernel<<<(n_pad + 255) / 256, 256, 0, c->stream>>>(a, b, n_pad, cl.pts.p);
+    RG_CUDA(c, cudaGetLastError());
+  }
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));      // msg may be pageable and reused by the caller
+  if (n_corner) *n_corner = (int32_t)P.corner.n_points;
+  if (n_surface) *n_surface = (int32_t)P.surface.n_points;
   if (which == RG_TARGET) c->voxel_ok = false;
   c->st_ok = false; c->have_corr = false;
   if (which == RG_SOURCE) c->shard_lo = c->shard_hi = 0;

@@ -242,6 +242,32 @@ class RotVGICP:
         self._keep[which] = None
         return nc.value, ns.value
 
+    def cloudInfoSerialize(self, stage: int, seq: int = 0, stamp_sec: int = 0, stamp_nsec: int = 0, frame_id: str = "", scalars9=None,
+                           covariance=None, odom_available: bool = False) -> bytes:
+        """ROS1 wire image of rolo/CloudInfoStamp for the frame last run through frontEndFrame: stage 0 as imageProjection
+        publishes it (imageProjection.cpp:507-512), stage 1 as featureExtraction does (featureExtraction.cpp:268-287)."""
+        hdr = capi.MsgHeader(seq, stamp_sec, stamp_nsec, frame_id.encode())
+        sc = capi.CloudInfoScalars()
+        s9 = np.zeros(9, np.float32) if scalars9 is None else np.asarray(scalars9, np.float32)
+        sc.start_orientation, sc.end_orientation, sc.orientation_diff = float(s9[0]), float(s9[1]), float(s9[2])
+        for k in range(6): sc.initial_guess[k] = float(s9[3 + k])
+        cov = np.zeros(0, np.float32) if covariance is None else np.ascontiguousarray(covariance, np.float32)
+        sc.covariance = cov.ctypes.data_as(C.POINTER(C.c_float)) if cov.size else None
+        sc.n_covariance = cov.size; sc.odom_available = 1 if odom_available else 0
+        n = C.c_size_t()
+        self._ck(self._L.rg_cloud_info_serialize(self._h, stage, C.byref(hdr), C.byref(sc), None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=np.uint8)
+        self._ck(self._L.rg_cloud_info_serialize(self._h, stage, C.byref(hdr), C.byref(sc), C.c_void_p(out.ctypes.data), n.value, C.byref(n)))
+        return out.tobytes()
+
+    def setInputFromCloudInfo(self, which: int, msg: bytes):
+        """Consumer edge (lidarOdometry.cpp:521-524): corner + surface of a serialised CloudInfoStamp become the source/target."""
+        a = np.frombuffer(msg, dtype=np.uint8)
+        nc = C.c_int32(); ns = C.c_int32()
+        self._ck(self._L.rg_set_input_from_cloud_info(self._h, which, C.c_void_p(a.ctypes.data), a.size, C.byref(nc), C.byref(ns)))
+        self._keep[which] = None
+        return nc.value, ns.value
+
     def setSourceShard(self, lo: int, hi: int): self._ck(self._L.rg_set_source_shard(self._h, lo, hi))
 
     def shardExport(self) -> bytes:
