@@ -244,6 +244,26 @@ int rg_cloud_info_serialize(rg_ctx*, int stage, const rg_msg_header* hdr, const 
  * source or target cloud; the point records are unpacked on the device. */
 int rg_set_input_from_cloud_info(rg_ctx*, int which, const uint8_t* msg, size_t len, int32_t* n_corner, int32_t* n_surface);
 
+/* ---- backMapping scan-to-map optimisation (src/backMapping.cpp:681-1054) -------------------------------
+ * LOAM-style refinement of the odometry pose against the local feature map: per scan feature a 5-NN search in the
+ * corner / surface map, a line (PCA) or plane (QR) fit, a point-to-line / point-to-plane coefficient, the 6x6 normal
+ * equations, a Gauss-Newton step with the degeneracy projection of the first iteration. One fused kernel per iteration
+ * (scan2map.cu); the 6x6 algebra stays on the host. Pose vectors are the reference's transformTobeMapped:
+ * {roll, pitch, yaw, x, y, z} float. Clouds: xyz at the start of each record, stride_bytes apart.
+ *   rg_s2m_set_map    = kdtreeCornerFromMap/kdtreeSurfFromMap->setInputCloud(laserCloud{Corner,Surf}FromMapDS)  (:689-690)
+ *   rg_s2m_set_scan   = laserCloudCornerLastDS / laserCloudSurfLastDS                                            (:670-678)
+ *   rg_s2m_linearize  = cornerOptimization + surfOptimization + combineOptimizationCoeffs + matAtA/matAtB at one pose
+ *                       (:719-1006); n_selected = laserCloudSelNum
+ *   rg_s2m_get_coefficients = coeffSel / laserCloudOri*Flag of the last evaluation, per scan point (4 floats, 1 byte)
+ *   rg_s2m_optimize   = scan2MapOptimization's loop (:691-703) without transformUpdate(); enough_features = 0 reproduces
+ *                       the "Not enough features!" branch (:687,705-707), tf is then left untouched. */
+typedef struct rg_s2m_result { int32_t iterations, converged, degenerate, enough_features; } rg_s2m_result;
+int rg_s2m_set_map(rg_ctx*, const float* corner, size_t n_corner, const float* surf, size_t n_surf, size_t stride_bytes);
+int rg_s2m_set_scan(rg_ctx*, const float* corner, size_t n_corner, const float* surf, size_t n_surf, size_t stride_bytes);
+int rg_s2m_linearize(rg_ctx*, const float tf[6], float AtA[36], float AtB[6], int32_t* n_selected);
+int rg_s2m_get_coefficients(rg_ctx*, float* coeff_corner, uint8_t* flag_corner, float* coeff_surf, uint8_t* flag_surf);
+int rg_s2m_optimize(rg_ctx*, float tf[6], int max_iterations, int edge_feature_min, int surf_feature_min, rg_s2m_result* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,6 +28,13 @@ int rgt_build_schedule(const int* n_points, int n_pairs, int grid, int* sched);
 void rgt_se3_exp(const double a[6], double T[16]);
 void rgt_ldlt_solve(const double* A, const double* rhs, int n, double* x);
 
+/* scan-to-map host algebra (s2m_math.cuh): W descending + rows of V eigenvectors; least squares by Householder QR;
+ * inverse by LU (returns 0 when singular); pcl::getTransformation rows */
+void rgt_s2m_eigen(int n /* 3 or 6 */, const float* A, float* W, float* V);
+void rgt_s2m_qr_solve(int rows, int cols /* 5x3 pivoted or 6x6 */, const float* A, const float* b, float* x);
+int  rgt_s2m_invert6(const float* A, float* inv);
+void rgt_s2m_get_transformation(const float tf[6], float t12[12]);
+
 #ifdef __cplusplus
 }
 #endif

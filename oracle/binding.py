@@ -297,6 +297,54 @@ def cloud_info_features(msg: bytes) -> tuple[np.ndarray, int, int]:
     return out, nc.value, ns.value
 
 
+class Scan2Map:
+    """backMapping's scan-to-map optimisation (scan2map_oracle.cpp; backMapping.cpp:681-1054). Clouds are (n, >=3) float32."""
+
+    def __init__(self, threads: int = 0):
+        self.L = lib()
+        self.L.ro_s2m_create.restype = C.c_void_p
+        self.h = C.c_void_p(self.L.ro_s2m_create())
+        self.L.ro_s2m_set_num_threads(self.h, threads)
+        self.n_corner = self.n_surf = 0
+
+    def __del__(self):
+        try:
+            self.L.ro_s2m_destroy(self.h)
+        except Exception:
+            pass
+
+    @staticmethod
+    def _c(a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        return a, C.c_void_p(a.ctypes.data), C.c_size_t(a.shape[0]), a.shape[1]
+
+    def setMap(self, corner, surf):
+        c, cp, cn, cs = self._c(corner); s, sp, sn, ss = self._c(surf)
+        assert cs == ss
+        self.L.ro_s2m_set_map(self.h, cp, cn, sp, sn, C.c_size_t(cs))
+
+    def setScan(self, corner, surf):
+        c, cp, cn, cs = self._c(corner); s, sp, sn, ss = self._c(surf)
+        assert cs == ss
+        self.n_corner, self.n_surf = c.shape[0], s.shape[0]
+        self.L.ro_s2m_set_scan(self.h, cp, cn, sp, sn, C.c_size_t(cs))
+
+    def linearize(self, tf6):
+        tf = np.ascontiguousarray(tf6, dtype=np.float32)
+        AtA = np.empty(36, np.float32); AtB = np.empty(6, np.float32)
+        cc = np.empty((self.n_corner, 4), np.float32); fc = np.empty(self.n_corner, np.uint8)
+        cs = np.empty((self.n_surf, 4), np.float32); fs = np.empty(self.n_surf, np.uint8)
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+        n = self.L.ro_s2m_linearize(self.h, vp(tf), vp(AtA), vp(AtB), vp(cc), vp(fc), vp(cs), vp(fs))
+        return {"AtA": AtA.reshape(6, 6), "AtB": AtB, "n_sel": n, "coeff_corner": cc, "flag_corner": fc, "coeff_surf": cs, "flag_surf": fs}
+
+    def optimize(self, tf6, max_iter=30, edge_min=10, surf_min=100):
+        tf = np.array(tf6, dtype=np.float32)
+        conv, deg = C.c_int(), C.c_int()
+        it = self.L.ro_s2m_optimize(self.h, C.c_void_p(tf.ctypes.data), max_iter, edge_min, surf_min, C.byref(conv), C.byref(deg))
+        return {"pose": tf, "iterations": it, "converged": bool(conv.value), "degenerate": bool(deg.value)}
+
+
 # ---- oracle/_ref: the REFERENCE's own rot_gicp sources compiled against oracle/ref_shim (see oracle/Makefile) ----
 _REF_PATH = os.path.join(_HERE, "_ref", "librolo_ref.so")
 _ref = None

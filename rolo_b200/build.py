@@ -23,7 +23,9 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
           "--expt-relaxed-constexpr", "-Xptxas", "-v", "-I", os.path.join(HERE, "..", "include")]
 EXTRA = os.environ.get("ROLO_NVCC_FLAGS", "").split()
-SOURCES = ["linearize.cu", "voxelmap.cu", "covariance.cu", "frontend.cu", "context.cu", "testing_hooks.cu"]
+SOURCES = ["linearize.cu", "voxelmap.cu", "covariance.cu", "frontend.cu", "scan2map.cu", "context.cu", "testing_hooks.cu"]
+# scan2map.cu restates float arithmetic of the reference operation by operation: no FMA contraction there
+PER_FILE = {"scan2map.cu": ["-fmad=false"]}
 
 
 def _deps():
@@ -39,7 +41,7 @@ def _stale(target: str, deps) -> bool:
 
 def _compile(src: str, verbose: bool) -> str:
     obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
-    cmd = [NVCC, *ARCH, *COMMON, *EXTRA, "-c", os.path.join(SRC, src), "-o", obj]
+    cmd = [NVCC, *ARCH, *COMMON, *PER_FILE.get(src, []), *EXTRA, "-c", os.path.join(SRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(obj + ".log", "w") as f:

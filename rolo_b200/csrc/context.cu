@@ -21,6 +21,8 @@
 #include "linearize.cuh"
 #include "lsq_host.hpp"
 #include "cloud_info.hpp"
+#include "scan2map.cuh"
+#include "s2m_math.cuh"
 #include "voxelmap.cuh"
 
 using namespace rolo;
@@ -267,6 +269,15 @@ struct rg_ctx {
   DevBuf<int> fe_owner, fe_row_count, fe_col, fe_start, fe_end, fe_counts, fe_picked, fe_label, fe_corner_cnt, fe_surf_cnt;
   DevBuf<float> fe_range_image, fe_prange, fe_curv;
   DevBuf<float4> fe_full, fe_extracted, fe_corner_ring, fe_surf_ring, fe_corner_out, fe_surf_out;
+  // scan-to-map optimisation (backMapping.cpp:681-1054): clouds 0/1 = corner/surface feature MAP, 2/3 = corner/surface SCAN
+  Cloud s2m_cloud[4];
+  DevBuf<float4> s2m_sorted[2], s2m_coeff[2];
+  DevBuf<unsigned long long> s2m_codes[2];
+  DevBuf<int> s2m_bucket[2], s2m_bbox[2];
+  DevBuf<unsigned char> s2m_flag[2];
+  DevBuf<double> s2m_partial, s2m_result;
+  DevBuf<unsigned> s2m_counter;
+  bool s2m_map_ok = false, s2m_scan_ok = false, s2m_lin_ok = false;
   DevBuf<unsigned char> fe_wire;        // packed PointXYZI records / uploaded message sections (cloud_info.hpp)
   bool fe_frame_ok = false;             // rg_front_end_frame products are resident
   int fe_n_scan = 0, fe_n[3] = {0, 0, 0};   // extracted, corner, surface counts of that frame
@@ -704,6 +715,9 @@ void rg_destroy(rg_ctx* c) {
   c->fe_counts.release(); c->fe_picked.release(); c->fe_label.release(); c->fe_corner_cnt.release(); c->fe_surf_cnt.release();
   c->fe_range_image.release(); c->fe_prange.release(); c->fe_curv.release(); c->fe_full.release(); c->fe_extracted.release();
   c->fe_corner_ring.release(); c->fe_surf_ring.release(); c->fe_corner_out.release(); c->fe_surf_out.release(); c->fe_wire.release();
+  for (int k = 0; k < 4; k++) c->s2m_cloud[k].release();
+  for (int k = 0; k < 2; k++) { c->s2m_sorted[k].release(); c->s2m_coeff[k].release(); c->s2m_codes[k].release(); c->s2m_bucket[k].release(); c->s2m_bbox[k].release(); c->s2m_flag[k].release(); }
+  c->s2m_partial.release(); c->s2m_result.release(); c->s2m_counter.release();
   c->corr.release(); c->partials.release(); c->counter.release(); c->result_dev.release(); c->st_dev.release(); c->staging.release(); c->sched_dev.release();
   for (int p = 0; p < XCHG_MAX_RANKS; p++) if (c->peer_xchg[p] && c->peer_xchg[p] != c->xchg) cudaIpcCloseMemHandle(c->peer_xchg[p]);
   if (c->xchg) cudaFree(c->xchg);
@@ -1511,5 +1525,150 @@ extern "C" int rg_set_input_from_cloud_info(rg_ctx* c, int which, const uint8_t*
   if (which == RG_TARGET) c->voxel_ok = false;
   c->st_ok = false; c->have_corr = false;
   if (which == RG_SOURCE) c->shard_lo = c->shard_hi = 0;
+  return RG_OK;
+}
+
+// ---- backMapping scan-to-map optimisation (backMapping.cpp:681-1054) ------------------------------
+
+extern "C" int rg_s2m_set_map(rg_ctx* c, const float* corner, size_t n_corner, const float* surf, size_t n_surf, size_t stride_bytes) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  c->s2m_map_ok = false; c->s2m_lin_ok = false;
+  const float* src[2] = {corner, surf}; const size_t cnt[2] = {n_corner, n_surf};
+  for (int m = 0; m < 2; m++) {
+    if (int rc = upload_cloud(c, c->s2m_cloud[m], src[m], cnt[m], stride_bytes)) return rc;
+    const int n = (int)cnt[m];
+    if (n == 0) continue;
+    // kdtree*FromMap->setInputCloud (backMapping.cpp:689-690): here the Morton index of covariance.cu
+    RG_CUDA(c, c->codes_in.ensure(c->device, n)); RG_CUDA(c, c->idx_in.ensure(c->device, n)); RG_CUDA(c, c->idx_out.ensure(c->device, n));
+    RG_CUDA(c, c->s2m_codes[m].ensure(c->device, n)); RG_CUDA(c, c->s2m_sorted[m].ensure(c->device, n));
+    RG_CUDA(c, c->s2m_bbox[m].ensure(c->device, 8)); RG_CUDA(c, c->s2m_bucket[m].ensure(c->device, cov_bucket_table_entries()));
+    const size_t tb = cov_cub_temp_bytes(n);
+    RG_CUDA(c, c->cub_temp.ensure(c->device, tb));
+    CovScratch sc;
+    sc.codes_in = c->codes_in.p; sc.codes_out = c->s2m_codes[m].p; sc.idx_in = c->idx_in.p; sc.idx_out = c->idx_out.p; sc.sorted = c->s2m_sorted[m].p;
+    sc.cub_temp = c->cub_temp.p; sc.cub_temp_bytes = tb; sc.bbox = c->s2m_bbox[m].p; sc.bucket_start = c->s2m_bucket[m].p;
+    RG_CUDA(c, launch_sort_cloud(c->s2m_cloud[m].pts.p, n, sc, true, c->stream));
+    g_launches += 5;
+  }
+  c->s2m_map_ok = true;
+  return RG_OK;
+}
+
+extern "C" int rg_s2m_set_scan(rg_ctx* c, const float* corner, size_t n_corner, const float* surf, size_t n_surf, size_t stride_bytes) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  c->s2m_scan_ok = false; c->s2m_lin_ok = false;
+  // the intensity column is not used by the optimisation: xyz only
+  if (int rc = upload_cloud(c, c->s2m_cloud[2], corner, n_corner, stride_bytes)) return rc;
+  if (int rc = upload_cloud(c, c->s2m_cloud[3], surf, n_surf, stride_bytes)) return rc;
+  for (int m = 0; m < 2; m++) {
+    RG_CUDA(c, c->s2m_coeff[m].ensure(c->device, std::max(c->s2m_cloud[2 + m].n, 1)));
+    RG_CUDA(c, c->s2m_flag[m].ensure(c->device, std::max(c->s2m_cloud[2 + m].n, 1)));
+  }
+  c->s2m_scan_ok = true;
+  return RG_OK;
+}
+
+// one kernel launch = cornerOptimization + surfOptimization + combineOptimizationCoeffs + the AtA/AtB assembly at pose tf
+static int s2m_evaluate(rg_ctx* c, const float tf[6], float AtA[36], float AtB[6], int* n_sel) {
+  if (!c->s2m_map_ok || !c->s2m_scan_ok) return set_err(c, RG_ERR_INVALID, "scan-to-map: call rg_s2m_set_map and rg_s2m_set_scan first");
+  RG_CUDA(c, c->s2m_partial.ensure(c->device, (size_t)S2M_MAX_BLOCKS * S2M_RES));
+  RG_CUDA(c, c->s2m_result.ensure(c->device, S2M_RES));
+  if (!c->s2m_counter.p) {
+    RG_CUDA(c, c->s2m_counter.ensure(c->device, 1));
+    RG_CUDA(c, cudaMemsetAsync(c->s2m_counter.p, 0, sizeof(unsigned), c->stream));
+  }
+  S2MLaunch L;
+  for (int m = 0; m < 2; m++) {
+    L.map[m].pts = c->s2m_cloud[m].pts.p; L.map[m].sorted = c->s2m_sorted[m].p; L.map[m].codes = c->s2m_codes[m].p;
+    L.map[m].bucket_start = c->s2m_bucket[m].p; L.map[m].bbox = c->s2m_bbox[m].p; L.map[m].n = c->s2m_cloud[m].n;
+    L.scan[m] = c->s2m_cloud[2 + m].pts.p; L.n_scan[m] = c->s2m_cloud[2 + m].n;
+    L.coeff[m] = c->s2m_coeff[m].p; L.flag[m] = c->s2m_flag[m].p;
+  }
+  s2m::get_transformation(tf, L.t);
+  // LMOptimization's six sines / cosines (backMapping.cpp:949-954), evaluated on the host like the reference does
+  L.sc[0] = sinf(tf[1]); L.sc[1] = cosf(tf[1]); L.sc[2] = sinf(tf[2]); L.sc[3] = cosf(tf[2]); L.sc[4] = sinf(tf[0]); L.sc[5] = cosf(tf[0]);
+  L.partial = c->s2m_partial.p; L.counter = c->s2m_counter.p; L.result = c->s2m_result.p;
+  RG_CUDA(c, launch_scan2map(L, c->stream));
+  g_launches++;
+  double r[S2M_RES];
+  RG_CUDA(c, cudaMemcpyAsync(r, c->s2m_result.p, sizeof(r), cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  int t = 0;
+  for (int a = 0; a < 6; a++) for (int b = a; b < 6; b++, t++) AtA[a * 6 + b] = AtA[b * 6 + a] = (float)r[t];   // cv::gemm: double sums, float result
+  for (int a = 0; a < 6; a++) AtB[a] = (float)r[21 + a];
+  *n_sel = (int)(r[27] + 0.5);
+  c->s2m_lin_ok = true;
+  return RG_OK;
+}
+
+extern "C" int rg_s2m_linearize(rg_ctx* c, const float tf[6], float AtA[36], float AtB[6], int32_t* n_selected) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (!tf || !AtA || !AtB || !n_selected) return set_err(c, RG_ERR_INVALID, "rg_s2m_linearize: null argument");
+  int n = 0;
+  if (int rc = s2m_evaluate(c, tf, AtA, AtB, &n)) return rc;
+  *n_selected = n;
+  return RG_OK;
+}
+
+extern "C" int rg_s2m_get_coefficients(rg_ctx* c, float* coeff_corner, uint8_t* flag_corner, float* coeff_surf, uint8_t* flag_surf) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (!c->s2m_lin_ok) return set_err(c, RG_ERR_INVALID, "rg_s2m_get_coefficients: no evaluation yet");
+  float* cf[2] = {coeff_corner, coeff_surf}; uint8_t* fl[2] = {flag_corner, flag_surf};
+  for (int m = 0; m < 2; m++) {
+    const int n = c->s2m_cloud[2 + m].n;
+    if (n == 0) continue;
+    if (cf[m]) RG_CUDA(c, cudaMemcpyAsync(cf[m], c->s2m_coeff[m].p, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (fl[m]) RG_CUDA(c, cudaMemcpyAsync(fl[m], c->s2m_flag[m].p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+  }
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RG_OK;
+}
+
+// scan2MapOptimization (backMapping.cpp:681-710) + LMOptimization (:937-1054); transformUpdate()'s IMU blend is not part of it
+extern "C" int rg_s2m_optimize(rg_ctx* c, float tf[6], int max_iterations, int edge_feature_min, int surf_feature_min, rg_s2m_result* out) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (!tf || !out || max_iterations < 0) return set_err(c, RG_ERR_INVALID, "rg_s2m_optimize: bad arguments");
+  if (!c->s2m_map_ok || !c->s2m_scan_ok) return set_err(c, RG_ERR_INVALID, "scan-to-map: call rg_s2m_set_map and rg_s2m_set_scan first");
+  out->iterations = 0; out->converged = 0; out->degenerate = 0; out->enough_features = 0;
+  if (!(c->s2m_cloud[2].n > edge_feature_min && c->s2m_cloud[3].n > surf_feature_min)) return RG_OK;   // "Not enough features!" (:687,705-707)
+  out->enough_features = 1;
+  bool degenerate = false;
+  float matP[36];
+  for (int iter = 0; iter < max_iterations; iter++) {
+    float AtA[36], AtB[6], X[6];
+    int sel = 0;
+    if (int rc = s2m_evaluate(c, tf, AtA, AtB, &sel)) return rc;
+    out->iterations++;
+    if (sel < 50) continue;                                                       // :956-958
+    { float A[36], b[6]; std::memcpy(A, AtA, sizeof(A)); std::memcpy(b, AtB, sizeof(b)); s2m::qr_solve<6, 6, false>(A, b, X); }   // cv::solve(DECOMP_QR)
+    if (iter == 0) {                                                              // degeneracy analysis, first iteration only (:1008-1029)
+      float A[36], E[6], V[36], V2[36], Vi[36];
+      std::memcpy(A, AtA, sizeof(A));
+      s2m::jacobi_eigen<6>(A, E, V);
+      std::memcpy(V2, V, sizeof(V2));
+      degenerate = false;
+      for (int i = 5; i >= 0; i--) {
+        if (E[i] < 100.f) { for (int j = 0; j < 6; j++) V2[i * 6 + j] = 0.f; degenerate = true; } else break;
+      }
+      if (!s2m::invert_lu<6>(V, Vi)) std::memset(Vi, 0, sizeof(Vi));
+      for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) { double acc = 0.0; for (int k = 0; k < 6; k++) acc += (double)Vi[a * 6 + k] * (double)V2[k * 6 + b]; matP[a * 6 + b] = (float)acc; }
+    }
+    if (degenerate) {
+      float X2[6]; std::memcpy(X2, X, sizeof(X2));
+      for (int a = 0; a < 6; a++) { double acc = 0.0; for (int k = 0; k < 6; k++) acc += (double)matP[a * 6 + k] * (double)X2[k]; X[a] = (float)acc; }
+    }
+    for (int a = 0; a < 6; a++) tf[a] += X[a];
+    const float r0 = X[0] * 57.29578f, r1 = X[1] * 57.29578f, r2 = X[2] * 57.29578f, c0 = X[3] * 100, c1 = X[4] * 100, c2 = X[5] * 100;
+    const float deltaR = (float)std::sqrt((double)r0 * r0 + (double)r1 * r1 + (double)r2 * r2);
+    const float deltaT = (float)std::sqrt((double)c0 * c0 + (double)c1 * c1 + (double)c2 * c2);
+    if ((double)deltaR < 0.05 && (double)deltaT < 0.05) { out->converged = 1; break; }
+  }
+  out->degenerate = degenerate ? 1 : 0;
   return RG_OK;
 }

@@ -16,6 +16,7 @@
 // CPU oracle bit for bit.
 
 #include "covariance.cuh"
+#include "morton.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <float.h>
@@ -24,12 +25,6 @@
 namespace rolo {
 
 namespace {
-
-constexpr int MORTON_BITS = 13;           // bits per axis: 39-bit codes = 5 radix passes; finest cell = extent / 8192
-constexpr int CODE_BITS = 3 * MORTON_BITS;
-
-__device__ __forceinline__ int float_to_ordered(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7FFFFFFF; }
-__device__ __forceinline__ float ordered_to_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
 
 __global__ void bbox_init_kernel(int* bbox) {
   if (threadIdx.x < 3) bbox[threadIdx.x] = INT_MAX;
@@ -67,45 +62,6 @@ __global__ void bbox_kernel(const float4* __restrict__ pts, int n, int* bbox) {
   }
 }
 
-struct Quant {           // derived from the bbox on the fly by every kernel (no host round trip)
-  double mn[3];
-  double scale;          // finest cells per metre
-  double cell;           // finest cell size (metres)
-};
-
-__device__ __forceinline__ Quant make_quant(const int* bbox) {
-  Quant q;
-  double ext = 0.0;
-  #pragma unroll
-  for (int d = 0; d < 3; d++) {
-    q.mn[d] = (double)ordered_to_float(bbox[d]);
-    ext = fmax(ext, (double)ordered_to_float(bbox[3 + d]) - q.mn[d]);
-  }
-  ext = fmax(ext, 1e-6) * (1.0 + 1e-6);
-  q.cell = ext / (double)(1 << MORTON_BITS);
-  q.scale = 1.0 / q.cell;
-  return q;
-}
-
-__device__ __forceinline__ unsigned long long expand21(unsigned v) {   // spread 21 bits to every third bit
-  unsigned long long x = v & 0x1FFFFFull;
-  x = (x | x << 32) & 0x1F00000000FFFFull;
-  x = (x | x << 16) & 0x1F0000FF0000FFull;
-  x = (x | x << 8) & 0x100F00F00F00F00Full;
-  x = (x | x << 4) & 0x10C30C30C30C30C3ull;
-  x = (x | x << 2) & 0x1249249249249249ull;
-  return x;
-}
-__device__ __forceinline__ unsigned long long morton3(unsigned x, unsigned y, unsigned z) {
-  return expand21(x) | (expand21(y) << 1) | (expand21(z) << 2);
-}
-__device__ __forceinline__ void quantize(const Quant& q, float x, float y, float z, unsigned& ix, unsigned& iy, unsigned& iz) {
-  const double m = (double)((1 << MORTON_BITS) - 1);
-  ix = (unsigned)fmin(fmax(floor(((double)x - q.mn[0]) * q.scale), 0.0), m);
-  iy = (unsigned)fmin(fmax(floor(((double)y - q.mn[1]) * q.scale), 0.0), m);
-  iz = (unsigned)fmin(fmax(floor(((double)z - q.mn[2]) * q.scale), 0.0), m);
-}
-
 __global__ void morton_kernel(const float4* __restrict__ pts, int n, const int* __restrict__ bbox,
                               unsigned long long* __restrict__ codes, int* __restrict__ idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -125,15 +81,6 @@ __global__ void gather_sorted_kernel(const float4* __restrict__ pts, const int* 
   float4 p = pts[i];
   p.w = __int_as_float(i);
   sorted[j] = p;
-}
-
-__device__ __forceinline__ int lower_bound_u64(const unsigned long long* __restrict__ a, int n, unsigned long long key) {
-  int lo = 0, hi = n;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
-  }
-  return lo;
 }
 
 __device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
@@ -252,10 +199,6 @@ __device__ void regularize(const double cov[6], int method, double out[6]) {
 // ---------------------------------------------------------------------------------------------------
 constexpr int KNN_QPW = 4;            // queries handled sequentially by one warp
 constexpr int KNN_CAND_CAP = 1024;    // prefer a finer level when the block holds more candidates than this
-constexpr int BUCKET_BITS = 18;       // top Morton bits indexed by the bucket table (octree level 6)
-constexpr int BUCKET_SHIFT = 3 * MORTON_BITS - BUCKET_BITS;
-constexpr int N_BUCKETS = 1 << BUCKET_BITS;
-
 // bucket_start[b] = first sorted position whose code has top bits >= b (b = 0 .. N_BUCKETS): every later
 // lower_bound only searches inside one bucket
 __global__ void bucket_table_kernel(const unsigned long long* __restrict__ codes, int n, int* __restrict__ bucket_start) {
@@ -263,38 +206,6 @@ __global__ void bucket_table_kernel(const unsigned long long* __restrict__ codes
   if (b > N_BUCKETS) return;
   bucket_start[b] = (b == N_BUCKETS) ? n : lower_bound_u64(codes, n, (unsigned long long)b << BUCKET_SHIFT);
 }
-
-__device__ __forceinline__ int lower_bound_bucketed(const unsigned long long* __restrict__ codes, const int* __restrict__ bucket_start,
-                                                    unsigned long long key) {
-  const unsigned long long top = key >> BUCKET_SHIFT;
-  if (top >= (unsigned long long)N_BUCKETS) return __ldg(bucket_start + N_BUCKETS);
-  int lo = __ldg(bucket_start + top);
-  if ((key & ((1ull << BUCKET_SHIFT) - 1ull)) == 0ull) return lo;     // bucket-aligned key (levels <= 6)
-  int hi = __ldg(bucket_start + top + 1);
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(codes + mid) < key) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-__device__ __forceinline__ unsigned compact21(unsigned long long x) {   // inverse of expand21
-  x &= 0x1249249249249249ull;
-  x = (x ^ (x >> 2)) & 0x10C30C30C30C30C3ull;
-  x = (x ^ (x >> 4)) & 0x100F00F00F00F00Full;
-  x = (x ^ (x >> 8)) & 0x1F0000FF0000FFull;
-  x = (x ^ (x >> 16)) & 0x1F00000000FFFFull;
-  x = (x ^ (x >> 32)) & 0x1FFFFFull;
-  return (unsigned)x;
-}
-
-// candidates are ordered by the packed key (float distance bits << 32 | index): distances are >= +0, so the
-// unsigned bit pattern is monotone, and the index breaks ties exactly like the oracle's (distance, index) order
-__device__ __forceinline__ void bitonic_cmpx(unsigned long long& key, int j2, bool take_min) {
-  const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, j2);
-  if (take_min == (other < key)) key = other;
-}
-constexpr unsigned long long KEY_INF = 0x7F7FFFFF7FFFFFFFull;            // (FLT_MAX, INT_MAX)
 
 __global__ void __launch_bounds__(256, 5)        // 48 registers: 40 warps/SM measured 4 % faster than 32
 knn_warp_kernel(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes, const int* __restrict__ bucket_start,
@@ -530,22 +441,30 @@ size_t cov_cub_temp_bytes(int n) {
   return bytes;
 }
 
+// bounding box -> Morton codes -> radix sort -> Morton-ordered copy (+ bucket table): the spatial index shared by the
+// covariance kNN and the scan-to-map 5-NN (scan2map.cu)
+cudaError_t launch_sort_cloud(const float4* pts, int n, const CovScratch& s, bool bucket_table, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const int tb = 256, nb = (n + tb - 1) / tb;
+  bbox_init_kernel<<<1, 32, 0, stream>>>(s.bbox);
+  bbox_kernel<<<min(nb, 148), tb, 0, stream>>>(pts, n, s.bbox);
+  morton_kernel<<<nb, tb, 0, stream>>>(pts, n, s.bbox, s.codes_in, s.idx_in);
+  size_t temp = s.cub_temp_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(s.cub_temp, temp, s.codes_in, s.codes_out, s.idx_in, s.idx_out, n, 0, 3 * MORTON_BITS, stream);
+  if (e != cudaSuccess) return e;
+  gather_sorted_kernel<<<nb, tb, 0, stream>>>(pts, s.idx_out, n, s.sorted);
+  if (bucket_table) bucket_table_kernel<<<(N_BUCKETS + 1 + tb - 1) / tb, tb, 0, stream>>>(s.codes_out, n, s.bucket_start);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_covariances(const CovLaunch& L, cudaStream_t stream) {
   if (L.n <= 0) return cudaSuccess;
   if (L.k > KCAP || L.k < 1 || L.n < L.k || !L.knn) return cudaErrorInvalidValue;
   const int n = L.n;
-  const int tb = 256, nb = (n + tb - 1) / tb;
-  bbox_init_kernel<<<1, 32, 0, stream>>>(L.s.bbox);
-  bbox_kernel<<<min(nb, 148), tb, 0, stream>>>(L.pts, n, L.s.bbox);
-  morton_kernel<<<nb, tb, 0, stream>>>(L.pts, n, L.s.bbox, L.s.codes_in, L.s.idx_in);
-  size_t temp = L.s.cub_temp_bytes;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(L.s.cub_temp, temp, L.s.codes_in, L.s.codes_out, L.s.idx_in, L.s.idx_out, n, 0,
-                                                  3 * MORTON_BITS, stream);
+  cudaError_t e = launch_sort_cloud(L.pts, n, L.s, L.k <= 32, stream);
   if (e != cudaSuccess) return e;
-  gather_sorted_kernel<<<nb, tb, 0, stream>>>(L.pts, L.s.idx_out, n, L.s.sorted);
   if (L.k <= 32) {
     const int queries_per_block = (256 / 32) * KNN_QPW;
-    bucket_table_kernel<<<(N_BUCKETS + 1 + tb - 1) / tb, tb, 0, stream>>>(L.s.codes_out, n, L.s.bucket_start);
     const int gb = (n + queries_per_block - 1) / queries_per_block;
     knn_warp_kernel<<<gb, 256, 0, stream>>>(L.s.sorted, L.s.codes_out, L.s.bucket_start, n, L.k, L.s.bbox, L.knn);
   } else {

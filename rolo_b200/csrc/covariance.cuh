@@ -30,5 +30,7 @@ struct CovLaunch {
 };
 
 cudaError_t launch_covariances(const CovLaunch& L, cudaStream_t stream);
+// spatial index only (bbox, Morton codes, sort, Morton-ordered copy, optional bucket table)
+cudaError_t launch_sort_cloud(const float4* pts, int n, const CovScratch& s, bool bucket_table, cudaStream_t stream);
 
 }  // namespace rolo

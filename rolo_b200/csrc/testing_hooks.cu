@@ -2,6 +2,7 @@
 #include "../../include/rolo_gicp_testing.h"
 #include "linearize.cuh"
 #include "lsq_host.hpp"
+#include "s2m_math.cuh"
 
 using namespace rolo;
 
@@ -40,5 +41,19 @@ int rgt_build_schedule(const int* n_points, int n_pairs, int grid, int* sched) {
 }
 void rgt_se3_exp(const double a[6], double T[16]) { host::se3_exp_mat4(a, T); }
 void rgt_ldlt_solve(const double* A, const double* rhs, int n, double* x) { host::ldlt_solve(A, rhs, n, x); }
+
+void rgt_s2m_eigen(int n, const float* A, float* W, float* V) {
+  float a[36];
+  for (int i = 0; i < n * n; i++) a[i] = A[i];
+  if (n == 3) s2m::jacobi_eigen<3>(a, W, V); else s2m::jacobi_eigen<6>(a, W, V);
+}
+void rgt_s2m_qr_solve(int rows, int cols, const float* A, const float* b, float* x) {
+  float a[36], bb[6];
+  for (int i = 0; i < rows * cols; i++) a[i] = A[i];
+  for (int i = 0; i < rows; i++) bb[i] = b[i];
+  if (rows == 5 && cols == 3) s2m::qr_solve<5, 3, true>(a, bb, x); else s2m::qr_solve<6, 6, false>(a, bb, x);
+}
+int rgt_s2m_invert6(const float* A, float* inv) { return s2m::invert_lu<6>(A, inv) ? 1 : 0; }
+void rgt_s2m_get_transformation(const float tf[6], float t12[12]) { s2m::get_transformation(tf, t12); }
 
 }  // extern "C"

@@ -224,3 +224,55 @@ def raw_frame(scene: dict, T_ws: np.ndarray, sensor: str = "os1-128", sigma: flo
     raw["ring"] = ring.astype(np.uint16)
     raw["time"] = (col.astype(np.float32) / cols) * 0.1
     return raw
+
+
+# ---- scan-to-map cases (backMapping.cpp:681-1054) -----------------------------------------------------------------
+
+def voxel_downsample(pts: np.ndarray, leaf: float) -> np.ndarray:
+    """Centroid per occupied voxel (what pcl::VoxelGrid computes); only used to build synthetic inputs."""
+    if pts.shape[0] == 0:
+        return pts.reshape(0, 4).astype(np.float32)
+    key = np.floor(pts[:, :3].astype(np.float64) / leaf).astype(np.int64)
+    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    inv = inv.reshape(-1)
+    out = np.zeros((cnt.shape[0], 4), dtype=np.float64)
+    np.add.at(out, inv, pts[:, :4].astype(np.float64))
+    out /= cnt[:, None]
+    return out.astype(np.float32)
+
+
+def pose6(T: np.ndarray) -> np.ndarray:
+    """4x4 -> (roll, pitch, yaw, x, y, z) float32, the reference's transformTobeMapped order (ZYX Euler angles)."""
+    R = T[:3, :3]
+    pitch = -np.arcsin(np.clip(R[2, 0], -1.0, 1.0))
+    roll = np.arctan2(R[2, 1], R[2, 2]); yaw = np.arctan2(R[1, 0], R[0, 0])
+    return np.array([roll, pitch, yaw, T[0, 3], T[1, 3], T[2, 3]], dtype=np.float32)
+
+
+def pose6_matrix(tf: np.ndarray) -> np.ndarray:
+    T = np.eye(4)
+    T[:3, :3] = rot_rpy(float(tf[0]), float(tf[1]), float(tf[2])); T[:3, 3] = tf[3:6]
+    return T
+
+
+def scan2map_case(features, sensor: str = "small", n_keyframes: int = 6, seed: int = 11, corner_leaf: float = 0.2, surf_leaf: float = 0.4,
+                  guess_deg: float = 1.0, guess_t: float = 0.15) -> dict:
+    """A local feature map assembled from `n_keyframes` keyframes (extractSurroundingKeyFrames' product: world-frame
+    corner/surface clouds, voxel-downsampled) and the downsampled features of a new scan with an offset initial guess.
+    `features(raw) -> (corner (n,4), surface (n,4))` is the front end to use (the GPU one or the oracle's)."""
+    scene = make_scene()
+    rng = np.random.default_rng(seed)
+    poses = [pose((0.3 * k, -0.2 * k, 4.0 * k), (0.8 * k, 0.15 * k, 0.0)) for k in range(n_keyframes + 1)]
+    mc, ms = [], []
+    for k in range(n_keyframes):
+        c, s = features(raw_frame(scene, poses[k], sensor, seed=seed + k))
+        for dst, f in ((mc, c), (ms, s)):
+            w = f.astype(np.float64).copy(); w[:, :3] = f[:, :3].astype(np.float64) @ poses[k][:3, :3].T + poses[k][:3, 3]
+            dst.append(w.astype(np.float32))
+    c, s = features(raw_frame(scene, poses[-1], sensor, seed=seed + 100))
+    T_true = poses[-1]
+    T_guess = T_true @ pose((guess_deg * rng.uniform(-1, 1), guess_deg * rng.uniform(-1, 1), guess_deg * rng.uniform(-1, 1)),
+                            tuple(guess_t * rng.uniform(-1, 1, 3)))
+    return {"map_corner": voxel_downsample(np.concatenate(mc), corner_leaf), "map_surf": voxel_downsample(np.concatenate(ms), surf_leaf),
+            "scan_corner": voxel_downsample(c, corner_leaf), "scan_surf": voxel_downsample(s, surf_leaf),
+            "pose_true": pose6(T_true), "pose_guess": pose6(T_guess), "T_true": T_true}

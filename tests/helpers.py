@@ -34,3 +34,12 @@ def make_both(tgt, src, polar=(0.175, 0.175, 2.0), uniform=None, method=capi.DIR
 def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def oracle_features(n_scan, horizon):
+    """raw frame -> (corner, surface) through the oracle's front end (for building scan-to-map inputs in CPU tests)."""
+    def f(raw):
+        p = ob.image_projection(raw, n_scan, horizon)
+        q = ob.feature_extraction(p, n_scan, horizon)
+        return q["corner"], q["surface"]
+    return f

@@ -1,0 +1,91 @@
+"""Scan-to-map optimisation (backMapping.cpp:681-1054) without a GPU:
+ * the oracle's restated third-party numerics against numpy / scipy,
+ * the product's host algebra (s2m_math.cuh through the testing hooks) BIT-EQUAL to the oracle's,
+ * the oracle's optimisation recovers a known pose on a synthetic map."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from rolo_b200 import capi, synth
+import helpers
+
+vp = lambda a: C.c_void_p(a.ctypes.data)
+
+
+def _cases(seed, count):
+    g = np.random.default_rng(seed)
+    for _ in range(count):
+        yield g
+
+
+def test_oracle_numerics_against_numpy():
+    L = ob.lib()
+    g = np.random.default_rng(0)
+    for n in (3, 6):
+        for _ in range(40):
+            B = g.standard_normal((n, n)).astype(np.float32); A = (B @ B.T).astype(np.float32)
+            W = np.empty(n, np.float32); V = np.empty((n, n), np.float32)
+            L.ro_s2m_eigen(n, vp(A), vp(W), vp(V))
+            w = np.linalg.eigvalsh(A.astype(np.float64))[::-1]
+            assert np.allclose(W, w, rtol=2e-5, atol=2e-5 * abs(w).max())
+            assert np.allclose(V @ V.T, np.eye(n), atol=1e-5) and np.allclose(V @ A @ V.T, np.diag(W), atol=5e-5 * abs(w).max())
+    for _ in range(40):
+        A = g.standard_normal((5, 3)).astype(np.float32); b = -np.ones(5, np.float32); x = np.empty(3, np.float32)
+        L.ro_s2m_qr_solve(5, 3, vp(A), vp(b), vp(x), 1)
+        assert np.allclose(x, np.linalg.lstsq(A.astype(np.float64), b.astype(np.float64), rcond=None)[0], rtol=1e-4, atol=1e-4)
+        A = g.standard_normal((6, 6)).astype(np.float32); A = A @ A.T + np.eye(6, dtype=np.float32); b = g.standard_normal(6).astype(np.float32)
+        x = np.empty(6, np.float32); L.ro_s2m_qr_solve(6, 6, vp(A), vp(b), vp(x), 0)
+        assert np.allclose(x, np.linalg.solve(A.astype(np.float64), b), rtol=2e-3, atol=2e-4)
+        inv = np.empty((6, 6), np.float32)
+        assert L.ro_s2m_invert(6, vp(A), vp(inv)) == 1 and np.allclose(inv, np.linalg.inv(A.astype(np.float64)), rtol=2e-3, atol=2e-4)
+    from scipy.spatial.transform import Rotation
+    tf = np.array([0.1, -0.2, 0.7, 1, 2, 3], np.float32); t = np.empty(12, np.float32)
+    L.ro_s2m_get_transformation(vp(tf), vp(t))
+    assert np.allclose(t.reshape(3, 4)[:, :3], Rotation.from_euler("ZYX", [0.7, -0.2, 0.1]).as_matrix(), atol=1e-6)
+    assert np.array_equal(t.reshape(3, 4)[:, 3], tf[3:])
+
+
+def test_product_host_algebra_is_bit_equal_to_the_oracle():
+    L = ob.lib(); P = capi.load()
+    g = np.random.default_rng(5)
+    for n in (3, 6):
+        for _ in range(60):
+            B = g.standard_normal((n, n)).astype(np.float32) * g.uniform(0.01, 30); A = (B @ B.T).astype(np.float32)
+            Wo = np.empty(n, np.float32); Vo = np.empty((n, n), np.float32); Wp = np.empty_like(Wo); Vp = np.empty_like(Vo)
+            L.ro_s2m_eigen(n, vp(A), vp(Wo), vp(Vo)); P.rgt_s2m_eigen(n, vp(A), vp(Wp), vp(Vp))
+            assert np.array_equal(Wo, Wp) and np.array_equal(Vo, Vp)
+    for _ in range(60):
+        A = (g.standard_normal((5, 3)) * g.uniform(0.1, 50) + g.uniform(-20, 20, 3)).astype(np.float32); b = -np.ones(5, np.float32)
+        xo = np.empty(3, np.float32); xp = np.empty(3, np.float32)
+        L.ro_s2m_qr_solve(5, 3, vp(A), vp(b), vp(xo), 1); P.rgt_s2m_qr_solve(5, 3, vp(A), vp(b), vp(xp))
+        assert np.array_equal(xo, xp)
+        A = g.standard_normal((6, 6)).astype(np.float32); A = (A @ A.T * 100).astype(np.float32); b = g.standard_normal(6).astype(np.float32)
+        xo = np.empty(6, np.float32); xp = np.empty(6, np.float32)
+        L.ro_s2m_qr_solve(6, 6, vp(A), vp(b), vp(xo), 0); P.rgt_s2m_qr_solve(6, 6, vp(A), vp(b), vp(xp))
+        assert np.array_equal(xo, xp)
+        io = np.empty((6, 6), np.float32); ip = np.empty((6, 6), np.float32)
+        assert L.ro_s2m_invert(6, vp(A), vp(io)) == P.rgt_s2m_invert6(vp(A), vp(ip)) == 1 and np.array_equal(io, ip)
+        tf = g.uniform(-3, 3, 6).astype(np.float32); to = np.empty(12, np.float32); tp = np.empty(12, np.float32)
+        L.ro_s2m_get_transformation(vp(tf), vp(to)); P.rgt_s2m_get_transformation(vp(tf), vp(tp))
+        assert np.array_equal(to, tp)
+    sing = np.zeros((6, 6), np.float32); io = np.empty((6, 6), np.float32)
+    assert L.ro_s2m_invert(6, vp(sing), vp(io)) == P.rgt_s2m_invert6(vp(sing), vp(io)) == 0
+
+
+def test_oracle_recovers_the_pose_on_a_synthetic_map():
+    case = synth.scan2map_case(helpers.oracle_features(32, 512), "small")
+    o = ob.Scan2Map(); o.setMap(case["map_corner"], case["map_surf"]); o.setScan(case["scan_corner"], case["scan_surf"])
+    lin = o.linearize(case["pose_guess"])
+    assert lin["n_sel"] == int(lin["flag_corner"].sum()) + int(lin["flag_surf"].sum()) > 1000
+    assert np.allclose(lin["AtA"], lin["AtA"].T)
+    res = o.optimize(case["pose_guess"])
+    assert res["converged"] and not res["degenerate"] and 1 <= res["iterations"] <= 30
+    assert np.max(np.abs(res["pose"][:3] - case["pose_true"][:3])) < 2e-3 and np.max(np.abs(res["pose"][3:] - case["pose_true"][3:])) < 1e-2
+    # thread-count invariance (the per-point work is independent; sums run in index order)
+    o1 = ob.Scan2Map(threads=1); o1.setMap(case["map_corner"], case["map_surf"]); o1.setScan(case["scan_corner"], case["scan_surf"])
+    assert np.array_equal(o1.optimize(case["pose_guess"])["pose"], res["pose"])
+    # too few features: the reference only warns and leaves the pose alone (backMapping.cpp:687,705-707)
+    few = o.optimize(case["pose_guess"], edge_min=10 ** 6)
+    assert few["iterations"] == -1 and np.array_equal(few["pose"], case["pose_guess"])
