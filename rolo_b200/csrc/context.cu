@@ -277,6 +277,7 @@ struct rg_ctx {
   DevBuf<unsigned char> s2m_flag[2];
   DevBuf<double> s2m_partial, s2m_result;
   DevBuf<unsigned> s2m_counter;
+  DevBuf<int> s2m_nn;
   bool s2m_map_ok = false, s2m_scan_ok = false, s2m_lin_ok = false;
   DevBuf<unsigned char> fe_wire;        // packed PointXYZI records / uploaded message sections (cloud_info.hpp)
   bool fe_frame_ok = false;             // rg_front_end_frame products are resident
@@ -717,7 +718,7 @@ void rg_destroy(rg_ctx* c) {
   c->fe_corner_ring.release(); c->fe_surf_ring.release(); c->fe_corner_out.release(); c->fe_surf_out.release(); c->fe_wire.release();
   for (int k = 0; k < 4; k++) c->s2m_cloud[k].release();
   for (int k = 0; k < 2; k++) { c->s2m_sorted[k].release(); c->s2m_coeff[k].release(); c->s2m_codes[k].release(); c->s2m_bucket[k].release(); c->s2m_bbox[k].release(); c->s2m_flag[k].release(); }
-  c->s2m_partial.release(); c->s2m_result.release(); c->s2m_counter.release();
+  c->s2m_partial.release(); c->s2m_result.release(); c->s2m_counter.release(); c->s2m_nn.release();
   c->corr.release(); c->partials.release(); c->counter.release(); c->result_dev.release(); c->st_dev.release(); c->staging.release(); c->sched_dev.release();
   for (int p = 0; p < XCHG_MAX_RANKS; p++) if (c->peer_xchg[p] && c->peer_xchg[p] != c->xchg) cudaIpcCloseMemHandle(c->peer_xchg[p]);
   if (c->xchg) cudaFree(c->xchg);
@@ -1573,7 +1574,9 @@ extern "C" int rg_s2m_set_scan(rg_ctx* c, const float* corner, size_t n_corner, 
 // one kernel launch = cornerOptimization + surfOptimization + combineOptimizationCoeffs + the AtA/AtB assembly at pose tf
 static int s2m_evaluate(rg_ctx* c, const float tf[6], float AtA[36], float AtB[6], int* n_sel) {
   if (!c->s2m_map_ok || !c->s2m_scan_ok) return set_err(c, RG_ERR_INVALID, "scan-to-map: call rg_s2m_set_map and rg_s2m_set_scan first");
-  RG_CUDA(c, c->s2m_partial.ensure(c->device, (size_t)S2M_MAX_BLOCKS * S2M_RES));
+  const size_t s2m_total = (size_t)c->s2m_cloud[2].n + c->s2m_cloud[3].n;
+  RG_CUDA(c, c->s2m_partial.ensure(c->device, ((s2m_total + S2M_FIT_THREADS_PER_BLOCK - 1) / S2M_FIT_THREADS_PER_BLOCK + 1) * S2M_RES));
+  RG_CUDA(c, c->s2m_nn.ensure(c->device, std::max<size_t>(s2m_total * 5, 8)));
   RG_CUDA(c, c->s2m_result.ensure(c->device, S2M_RES));
   if (!c->s2m_counter.p) {
     RG_CUDA(c, c->s2m_counter.ensure(c->device, 1));
@@ -1589,9 +1592,9 @@ static int s2m_evaluate(rg_ctx* c, const float tf[6], float AtA[36], float AtB[6
   s2m::get_transformation(tf, L.t);
   // LMOptimization's six sines / cosines (backMapping.cpp:949-954), evaluated on the host like the reference does
   L.sc[0] = sinf(tf[1]); L.sc[1] = cosf(tf[1]); L.sc[2] = sinf(tf[2]); L.sc[3] = cosf(tf[2]); L.sc[4] = sinf(tf[0]); L.sc[5] = cosf(tf[0]);
-  L.partial = c->s2m_partial.p; L.counter = c->s2m_counter.p; L.result = c->s2m_result.p;
+  L.nn = c->s2m_nn.p; L.partial = c->s2m_partial.p; L.counter = c->s2m_counter.p; L.result = c->s2m_result.p;
   RG_CUDA(c, launch_scan2map(L, c->stream));
-  g_launches++;
+  g_launches += 2;
   double r[S2M_RES];
   RG_CUDA(c, cudaMemcpyAsync(r, c->s2m_result.p, sizeof(r), cudaMemcpyDeviceToHost, c->stream));
   RG_CUDA(c, cudaStreamSynchronize(c->stream));

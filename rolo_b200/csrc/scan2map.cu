@@ -5,25 +5,28 @@
 // 5th neighbour is closer than 1 m, then either a PCA line test + point-to-line coefficient (corners, cv::eigen) or a plane
 // fit + point-to-plane coefficient (surfaces, Eigen QR); the selected points are compacted, a Jacobian row is built per
 // point and AtA (6x6) / AtB (6) are formed with cv::gemm.
-// Here: one WARP per scan point.
+// Here: two kernels per iteration — a warp per scan point for the 5-NN, then a thread per scan point for the fit.
 //   * 5-NN: both maps carry the Morton index of covariance.cu. Only neighbours within 1 m matter, so the search is a
 //     fixed-level 3x3x3 block scan at the level whose cells are >= 1.001 m: every point within 1 m of the query lies in
 //     that block, hence the five nearest are exact whenever the reference would accept the point, and a point the
 //     reference rejects (5th neighbour >= 1 m) finds fewer than five candidates. Lanes 0..26 locate the 27 cell ranges
 //     with two bucketed binary searches each; candidates are scanned 32 per step and merged into a sorted top list held
 //     one element per lane, ordered by (float distance, index) like the oracle's kd-tree.
-//   * the per-point algebra (3x3 Jacobi eigen / 5x3 pivoted Householder QR, s2m_math.cuh) runs redundantly in all lanes
-//     (same instruction count as one lane), float, no FMA contraction (-fmad=false for this file): results are bit-equal
-//     to the CPU oracle's.
-//   * no compaction: every lane owns one of the 21 + 6 + 1 sums (AtA upper triangle, AtB, count) and accumulates its
-//     product in double across the warp's points; warps -> block -> per-block partial -> the last block adds the
-//     partials in block order, so the result is deterministic.
+//     The block one level finer is tried first (a quarter of the candidates) and kept when its 5th distance is inside
+//     the radius that block provably covers.
+//   * the per-point algebra (3x3 Jacobi eigen / 5x3 pivoted Householder QR, s2m_math.cuh) runs one thread per point,
+//     float, no FMA contraction (-fmad=false for this file): results are bit-equal to the CPU oracle's.
+//   * no compaction: unselected points contribute zero rows; the 21 + 6 + 1 sums (AtA upper triangle, AtB, count) are
+//     formed in double: warp shuffle tree -> block -> per-block partial -> the last block adds the partials in block
+//     order, so the result is deterministic.
 // HBM traffic is a few hundred KB per iteration (the maps are L2-resident); the kernel is latency / instruction bound and
 // sized as a persistent grid over the scan points.
 
 #include "scan2map.cuh"
 #include "morton.cuh"
 #include "s2m_math.cuh"
+
+#include <algorithm>
 
 namespace rolo {
 
@@ -40,18 +43,11 @@ struct Params {
   float sc[6];
   float4* coeff[2];
   unsigned char* flag[2];
+  int* nn;
   double* partial;
   unsigned* counter;
   double* result;
 };
-
-// (row, column) of the upper-triangle entry a lane owns; lanes 21..26 own AtB, lane 27 the count
-__constant__ int c_row[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
-__constant__ int c_col[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
-
-__device__ __forceinline__ float pick6(float r0, float r1, float r2, float r3, float r4, float r5, int i) {
-  return i == 0 ? r0 : i == 1 ? r1 : i == 2 ? r2 : i == 3 ? r3 : i == 4 ? r4 : r5;
-}
 
 // shift (MORTON_BITS - level) of the coarsest-resolution level whose cells are still >= 1.001 m
 __device__ __forceinline__ int search_shift(const Quant& qn) {
@@ -60,11 +56,10 @@ __device__ __forceinline__ int search_shift(const Quant& qn) {
   return sh;
 }
 
-// exact five nearest map points within 1 m of `q`; returns true when five exist. idx[0..4] ascending by (distance, index).
-__device__ __forceinline__ bool five_nearest(const S2MMap& m, const Quant& qn, int sh, float qx, float qy, float qz, int lane, int idx[5]) {
+// one 3x3x3 block scan at shift `sh`: merges every candidate closer than 1 m into the sorted top list (one element per lane)
+__device__ __forceinline__ void scan_block(const S2MMap& m, int sh, unsigned ix, unsigned iy, unsigned iz, float qx, float qy, float qz, int lane,
+                                           unsigned long long& top) {
   const unsigned FULL = 0xffffffffu;
-  unsigned ix, iy, iz;
-  quantize(qn, qx, qy, qz, ix, iy, iz);
   const int cx = (int)(ix >> sh), cy = (int)(iy >> sh), cz = (int)(iz >> sh);
   const int L = MORTON_BITS - sh, ncell = 1 << L;
   int lo = 0, cnt = 0;
@@ -82,7 +77,7 @@ __device__ __forceinline__ bool five_nearest(const S2MMap& m, const Quant& qn, i
   for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
   const int total = __shfl_sync(FULL, incl, 31);
   const int excl = incl - cnt;
-  unsigned long long top = KEY_INF;
+  top = KEY_INF;
   #pragma unroll 1
   for (int base = 0; base < total; base += 32) {
     const int g = base + lane;
@@ -104,7 +99,7 @@ __device__ __forceinline__ bool five_nearest(const S2MMap& m, const Quant& qn, i
     }
     const unsigned long long kth = __shfl_sync(FULL, top, 4);
     unsigned msk = __ballot_sync(FULL, key < kth);
-    while (msk) {                                                       // at most a handful survive the 5th-distance filter
+    while (msk) {                                                       // few candidates survive the 5th-distance filter
       const int srcl = __ffs(msk) - 1;
       msk &= msk - 1;
       const unsigned long long ck = __shfl_sync(FULL, key, srcl);
@@ -113,6 +108,36 @@ __device__ __forceinline__ bool five_nearest(const S2MMap& m, const Quant& qn, i
       if (lane > pos) top = up; else if (lane == pos) top = ck;
     }
   }
+}
+
+// exact five nearest map points within 1 m of the query (one warp). `sh` is the level whose cells are >= 1.001 m: its
+// 3x3x3 block holds every point within 1 m. The block one level finer (a quarter of the candidates on a surface) is tried
+// first and accepted when its 5th distance lies inside the radius that block is guaranteed to cover.
+__device__ __forceinline__ bool five_nearest(const S2MMap& m, const Quant& qn, int sh, float qx, float qy, float qz, int lane, int idx[5]) {
+  const unsigned FULL = 0xffffffffu;
+  unsigned ix, iy, iz;
+  quantize(qn, qx, qy, qz, ix, iy, iz);
+  unsigned long long top = KEY_INF;
+  bool done = false;
+  if (sh > 0) {
+    const int sf = sh - 1;
+    scan_block(m, sf, ix, iy, iz, qx, qy, qz, lane, top);
+    const unsigned long long k5 = __shfl_sync(FULL, top, 4);
+    if (k5 != KEY_INF) {
+      const double sL = qn.cell * (double)(1 << sf);
+      const int ncell = 1 << (MORTON_BITS - sf);
+      const double rel[3] = {(double)qx - qn.mn[0], (double)qy - qn.mn[1], (double)qz - qn.mn[2]};
+      const int cc[3] = {(int)(ix >> sf), (int)(iy >> sf), (int)(iz >> sf)};
+      double rs = 1e300;
+      #pragma unroll
+      for (int dd = 0; dd < 3; dd++) {
+        if (cc[dd] - 1 >= 0) rs = fmin(rs, rel[dd] - (double)(cc[dd] - 1) * sL);
+        if (cc[dd] + 1 < ncell) rs = fmin(rs, (double)(cc[dd] + 2) * sL - rel[dd]);
+      }
+      done = rs > 0.0 && (double)__uint_as_float((unsigned)(k5 >> 32)) <= rs * rs * (1.0 - 1e-6);
+    }
+  }
+  if (!done) scan_block(m, sh, ix, iy, iz, qx, qy, qz, lane, top);
   const bool ok = __shfl_sync(FULL, top, 4) != KEY_INF;
   #pragma unroll
   for (int j = 0; j < 5; j++) idx[j] = (int)(unsigned)(__shfl_sync(FULL, top, j) & 0xFFFFFFFFull);
@@ -172,21 +197,44 @@ __device__ __forceinline__ bool surf_coeff(const float4 nb[5], float4 ori, float
   return (double)s > 0.1;
 }
 
+// stage 1, one WARP per scan point: pointAssociateToMap + nearestKSearch(5) -> five neighbour indices, or -1
 __global__ void __launch_bounds__(S2M_THREADS)
-s2m_kernel(const __grid_constant__ Params P) {
+s2m_knn_kernel(const __grid_constant__ Params P) {
+  const int lane = threadIdx.x & 31;
+  const int q = (int)((blockIdx.x * (unsigned)S2M_THREADS + threadIdx.x) >> 5);
+  const int n0 = P.n_scan[0], ntot = n0 + P.n_scan[1];
+  if (q >= ntot) return;
+  const int which = q >= n0 ? 1 : 0, i = q - which * n0;
+  int idx[5] = {-1, -1, -1, -1, -1};
+  if (P.map[which].n >= 5) {
+    const Quant qn = make_quant(P.map[which].bbox);
+    const int sh = search_shift(qn);
+    const float4 ori = __ldg(P.scan[which] + i);
+    const float sx = P.t[0] * ori.x + P.t[1] * ori.y + P.t[2] * ori.z + P.t[3];
+    const float sy = P.t[4] * ori.x + P.t[5] * ori.y + P.t[6] * ori.z + P.t[7];
+    const float sz = P.t[8] * ori.x + P.t[9] * ori.y + P.t[10] * ori.z + P.t[11];
+    if (!five_nearest(P.map[which], qn, sh, sx, sy, sz, lane, idx)) idx[0] = -1;
+  }
+  if (lane < 5) {
+    int v = idx[0];
+    #pragma unroll
+    for (int j = 1; j < 5; j++) if (lane == j) v = idx[0] < 0 ? -1 : idx[j];
+    P.nn[(size_t)q * 5 + lane] = v;
+  }
+}
+
+// stage 2, one THREAD per scan point: line / plane fit, coefficient, Jacobian row; 21 + 6 + 1 sums reduced warp -> block ->
+// per-block partial -> last block (block order): deterministic
+constexpr int S2M_FIT_THREADS = S2M_FIT_THREADS_PER_BLOCK;
+__global__ void __launch_bounds__(S2M_FIT_THREADS)
+s2m_fit_kernel(const __grid_constant__ Params P) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int gwarp = blockIdx.x * S2M_WARPS + warp, nwarps = gridDim.x * S2M_WARPS;
+  const int q = blockIdx.x * S2M_FIT_THREADS + threadIdx.x;
   const int n0 = P.n_scan[0], ntot = n0 + P.n_scan[1];
-  Quant qn[2]; int sh[2];
-  #pragma unroll
-  for (int w = 0; w < 2; w++) { if (P.map[w].n >= 5) { qn[w] = make_quant(P.map[w].bbox); sh[w] = search_shift(qn[w]); } else { qn[w] = Quant{}; sh[w] = 0; } }
-  const float srx = P.sc[0], crx = P.sc[1], sry = P.sc[2], cry = P.sc[3], srz = P.sc[4], crz = P.sc[5];
-  const int my_r = lane < 21 ? c_row[lane] : (lane < 27 ? lane - 21 : 0), my_c = lane < 21 ? c_col[lane] : 0;
-  double acc = 0.0;
-
-  #pragma unroll 1
-  for (int q = gwarp; q < ntot; q += nwarps) {
+  float row[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, bi = 0.f;
+  bool sel = false;
+  if (q < ntot) {
     const int which = q >= n0 ? 1 : 0, i = q - which * n0;
     const float4 ori = __ldg(P.scan[which] + i);
     // pointAssociateToMap (backMapping.cpp:293-299)
@@ -194,19 +242,19 @@ s2m_kernel(const __grid_constant__ Params P) {
     const float sy = P.t[4] * ori.x + P.t[5] * ori.y + P.t[6] * ori.z + P.t[7];
     const float sz = P.t[8] * ori.x + P.t[9] * ori.y + P.t[10] * ori.z + P.t[11];
     float4 coeff = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool sel = false;
-    int idx[5];
-    if (P.map[which].n >= 5 && five_nearest(P.map[which], qn[which], sh[which], sx, sy, sz, lane, idx)) {
+    const int* nn = P.nn + (size_t)q * 5;
+    if (__ldg(nn) >= 0) {
       float4 nb[5];
       #pragma unroll
-      for (int j = 0; j < 5; j++) nb[j] = __ldg(P.map[which].pts + idx[j]);
+      for (int j = 0; j < 5; j++) nb[j] = __ldg(P.map[which].pts + __ldg(nn + j));
       float4 cf;
       sel = which == 0 ? corner_coeff(nb, sx, sy, sz, cf) : surf_coeff(nb, ori, sx, sy, sz, cf);
       if (sel) coeff = cf;
     }
-    if (lane == 0) { P.coeff[which][i] = coeff; P.flag[which][i] = sel ? 1 : 0; }
+    P.coeff[which][i] = coeff; P.flag[which][i] = sel ? 1 : 0;
     if (sel) {
       // LMOptimization's Jacobian row (backMapping.cpp:968-1005): lidar -> camera axis swap, then back
+      const float srx = P.sc[0], crx = P.sc[1], sry = P.sc[2], cry = P.sc[3], srz = P.sc[4], crz = P.sc[5];
       const float px = ori.y, py = ori.z, pz = ori.x;
       const float cx = coeff.y, cy = coeff.z, cz = coeff.x;
       const float arx = (crx * sry * srz * px + crx * crz * sry * py - srx * sry * pz) * cx + (-srx * srz * px - crz * srx * py - crx * pz) * cy +
@@ -215,20 +263,39 @@ s2m_kernel(const __grid_constant__ Params P) {
                         ((-cry * crz - srx * sry * srz) * px + (cry * srz - crz * srx * sry) * py - crx * sry * pz) * cz;
       const float arz = ((crz * srx * sry - cry * srz) * px + (-cry * crz - srx * sry * srz) * py) * cx + (crx * crz * px - crx * srz * py) * cy +
                         ((sry * srz + cry * crz * srx) * px + (crz * sry - cry * srx * srz) * py) * cz;
-      const float ra = pick6(arz, arx, ary, cz, cx, cy, my_r);
-      const float rb = lane < 21 ? pick6(arz, arx, ary, cz, cx, cy, my_c) : -coeff.w;
-      if (lane < 27) acc += (double)ra * (double)rb; else if (lane == 27) acc += 1.0;
+      row[0] = arz; row[1] = arx; row[2] = ary; row[3] = cz; row[4] = cx; row[5] = cy;
+      bi = -coeff.w;
     }
   }
-
-  __shared__ double s_acc[S2M_WARPS][S2M_RES];
+  __shared__ double s_acc[S2M_FIT_THREADS / 32][S2M_RES];
   __shared__ bool s_last;
-  s_acc[warp][lane] = lane < 28 ? acc : 0.0;
+  int t = 0;
+  #pragma unroll
+  for (int a = 0; a < 6; a++) {
+    #pragma unroll
+    for (int b = a; b < 6; b++, t++) {
+      double v = (double)row[a] * (double)row[b];       // exact: float x float fits a double
+      #pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+      if (lane == 0) s_acc[warp][t] = v;
+    }
+  }
+  #pragma unroll
+  for (int a = 0; a < 6; a++) {
+    double v = (double)row[a] * (double)bi;
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if (lane == 0) s_acc[warp][21 + a] = v;
+  }
+  {
+    const unsigned m = __ballot_sync(FULL, sel);
+    if (lane == 0) { s_acc[warp][27] = (double)__popc(m); for (int k = 28; k < S2M_RES; k++) s_acc[warp][k] = 0.0; }
+  }
   __syncthreads();
   if (threadIdx.x < S2M_RES) {
     double v = 0.0;
     #pragma unroll
-    for (int w = 0; w < S2M_WARPS; w++) v += s_acc[w][threadIdx.x];
+    for (int w = 0; w < S2M_FIT_THREADS / 32; w++) v += s_acc[w][threadIdx.x];
     P.partial[(size_t)blockIdx.x * S2M_RES + threadIdx.x] = v;
   }
   __threadfence();
@@ -239,12 +306,11 @@ s2m_kernel(const __grid_constant__ Params P) {
     __threadfence();
     if (threadIdx.x < S2M_RES) {
       double v = 0.0;
-      for (unsigned b = 0; b < gridDim.x; b++) v += __ldcg(P.partial + (size_t)b * S2M_RES + threadIdx.x);   // block order: deterministic
+      for (unsigned b = 0; b < gridDim.x; b++) v += __ldcg(P.partial + (size_t)b * S2M_RES + threadIdx.x);   // block order
       P.result[threadIdx.x] = v;
     }
     if (threadIdx.x == 0) *P.counter = 0u;
   }
-  (void)FULL;
 }
 
 }  // namespace
@@ -254,11 +320,11 @@ cudaError_t launch_scan2map(const S2MLaunch& L, cudaStream_t stream) {
   for (int w = 0; w < 2; w++) { P.map[w] = L.map[w]; P.scan[w] = L.scan[w]; P.n_scan[w] = L.n_scan[w]; P.coeff[w] = L.coeff[w]; P.flag[w] = L.flag[w]; }
   for (int k = 0; k < 12; k++) P.t[k] = L.t[k];
   for (int k = 0; k < 6; k++) P.sc[k] = L.sc[k];
-  P.partial = L.partial; P.counter = L.counter; P.result = L.result;
+  P.nn = L.nn; P.partial = L.partial; P.counter = L.counter; P.result = L.result;
   const long long ntot = (long long)L.n_scan[0] + L.n_scan[1];
-  int grid = (int)((ntot + S2M_WARPS - 1) / S2M_WARPS);
-  grid = grid < 1 ? 1 : (grid > S2M_MAX_BLOCKS ? S2M_MAX_BLOCKS : grid);
-  s2m_kernel<<<grid, S2M_THREADS, 0, stream>>>(P);
+  if (ntot > 0) s2m_knn_kernel<<<(unsigned)((ntot * 32 + S2M_THREADS - 1) / S2M_THREADS), S2M_THREADS, 0, stream>>>(P);
+  const int fit_blocks = (int)std::max<long long>(1, (ntot + S2M_FIT_THREADS - 1) / S2M_FIT_THREADS);
+    s2m_fit_kernel<<<fit_blocks, S2M_FIT_THREADS, 0, stream>>>(P);
   return cudaGetLastError();
 }
 

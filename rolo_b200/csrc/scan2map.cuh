@@ -5,7 +5,7 @@
 namespace rolo {
 
 constexpr int S2M_RES = 32;        // doubles per result: 21 AtA (upper triangle, row-major) + 6 AtB + 1 count + pad
-constexpr int S2M_MAX_BLOCKS = 1184;
+constexpr int S2M_FIT_THREADS_PER_BLOCK = 128;   // partial[] needs ceil(n_scan_total / 128) x S2M_RES doubles
 
 struct S2MMap {                    // one Morton-indexed map cloud (covariance.cuh: launch_sort_cloud)
   const float4* pts;               // original order
@@ -24,7 +24,8 @@ struct S2MLaunch {
   float sc[6];                     // srx crx sry cry srz crz (LMOptimization, backMapping.cpp:949-954; host sinf/cosf)
   float4* coeff[2];                // coeffSel per scan point (x y z intensity), zero when not selected
   unsigned char* flag[2];          // laserCloudOri*Flag
-  double* partial;                 // [S2M_MAX_BLOCKS][S2M_RES]
+  int* nn;                         // [(n_scan[0] + n_scan[1]) x 5] neighbour indices (first = -1: rejected)
+  double* partial;                 // [ceil(n_scan_total / 128)][S2M_RES]
   unsigned* counter;               // ticket, zero before the first launch (the kernel re-arms it)
   double* result;                  // [S2M_RES]
 };
