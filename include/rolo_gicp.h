@@ -264,6 +264,21 @@ int rg_s2m_linearize(rg_ctx*, const float tf[6], float AtA[36], float AtB[6], in
 int rg_s2m_get_coefficients(rg_ctx*, float* coeff_corner, uint8_t* flag_corner, float* coeff_surf, uint8_t* flag_surf);
 int rg_s2m_optimize(rg_ctx*, float tf[6], int max_iterations, int edge_feature_min, int surf_feature_min, rg_s2m_result* out);
 
+/* ---- Scan Context place recognition (src/scancontext/Scancontext.cpp) ----------------------------------
+ * The context owns one SCManager. The 20 x 60 descriptor (max height per polar bin) and its ring / sector keys are built on
+ * the device; alignment, cosine distance and the candidate search are a few thousand flops and run on the host.
+ *   rg_sc_make_and_save = SCManager::makeAndSaveScancontextAndKeys(scan)      (Scancontext.cpp:151-250)
+ *   rg_sc_detect        = SCManager::detectLoopClosureID()                    (:253-344): loop_id (-1 = none), yaw difference
+ *   rg_sc_distance      = SCManager::distanceBtnScanContext(sc_i, sc_j)       (:116-148)
+ *   rg_sc_get           = polarcontexts_[index] (row-major [ring][sector]), its ring key (20) and sector key (60); index -1 = last
+ * lidar_height is Scancontext.h:80's LIDAR_HEIGHT (2.0 in the reference). */
+int rg_sc_make_and_save(rg_ctx*, const float* pts, size_t n, size_t stride_bytes, double lidar_height);
+int rg_sc_size(rg_ctx*);
+int rg_sc_clear(rg_ctx*);
+int rg_sc_get(rg_ctx*, int index, double* desc1200, double* ring_key20, double* sector_key60);
+int rg_sc_distance(rg_ctx*, int i, int j, double* dist, int32_t* shift);
+int rg_sc_detect(rg_ctx*, int32_t* loop_id, float* yaw_diff_rad);
+
 #ifdef __cplusplus
 }
 #endif

@@ -345,6 +345,44 @@ class Scan2Map:
         return {"pose": tf, "iterations": it, "converged": bool(conv.value), "degenerate": bool(deg.value)}
 
 
+class SCManager:
+    """Scan Context place recogniser (scancontext_oracle.cpp; src/scancontext/Scancontext.cpp)."""
+    LIDAR_HEIGHT = 2.0
+
+    def __init__(self):
+        self.L = lib()
+        self.L.ro_sc_create.restype = C.c_void_p
+        self.h = C.c_void_p(self.L.ro_sc_create())
+
+    def __del__(self):
+        try:
+            self.L.ro_sc_destroy(self.h)
+        except Exception:
+            pass
+
+    def makeAndSaveScancontextAndKeys(self, scan):
+        a = np.ascontiguousarray(scan, dtype=np.float32)
+        self.L.ro_sc_make_and_save(self.h, C.c_void_p(a.ctypes.data), C.c_size_t(a.shape[0]), C.c_size_t(a.shape[1]), C.c_double(self.LIDAR_HEIGHT))
+
+    def size(self): return self.L.ro_sc_size(self.h)
+
+    def get(self, index=-1):
+        d = np.empty((20, 60), np.float64); rk = np.empty(20, np.float64); sk = np.empty(60, np.float64)
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+        assert self.L.ro_sc_get(self.h, index, vp(d), vp(rk), vp(sk)) == 0
+        return d, rk, sk
+
+    def distanceBtnScanContext(self, i, j):
+        d = C.c_double(); s = C.c_int()
+        assert self.L.ro_sc_distance(self.h, i, j, C.byref(d), C.byref(s)) == 0
+        return d.value, s.value
+
+    def detectLoopClosureID(self):
+        yaw = C.c_float()
+        lid = self.L.ro_sc_detect(self.h, C.byref(yaw))
+        return lid, yaw.value
+
+
 # ---- oracle/_ref: the REFERENCE's own rot_gicp sources compiled against oracle/ref_shim (see oracle/Makefile) ----
 _REF_PATH = os.path.join(_HERE, "_ref", "librolo_ref.so")
 _ref = None

@@ -22,6 +22,8 @@
 #include "lsq_host.hpp"
 #include "cloud_info.hpp"
 #include "scan2map.cuh"
+#include "scancontext.cuh"
+#include "sc_host.hpp"
 #include "s2m_math.cuh"
 #include "voxelmap.cuh"
 
@@ -278,6 +280,11 @@ struct rg_ctx {
   DevBuf<double> s2m_partial, s2m_result;
   DevBuf<unsigned> s2m_counter;
   DevBuf<int> s2m_nn;
+  // Scan Context place recognition (src/scancontext/Scancontext.cpp): descriptor kernel + host manager
+  Cloud sc_cloud;
+  DevBuf<int> sc_bins;
+  DevBuf<double> sc_out;
+  sc::Manager sc_mgr;
   bool s2m_map_ok = false, s2m_scan_ok = false, s2m_lin_ok = false;
   DevBuf<unsigned char> fe_wire;        // packed PointXYZI records / uploaded message sections (cloud_info.hpp)
   bool fe_frame_ok = false;             // rg_front_end_frame products are resident
@@ -719,6 +726,7 @@ void rg_destroy(rg_ctx* c) {
   for (int k = 0; k < 4; k++) c->s2m_cloud[k].release();
   for (int k = 0; k < 2; k++) { c->s2m_sorted[k].release(); c->s2m_coeff[k].release(); c->s2m_codes[k].release(); c->s2m_bucket[k].release(); c->s2m_bbox[k].release(); c->s2m_flag[k].release(); }
   c->s2m_partial.release(); c->s2m_result.release(); c->s2m_counter.release(); c->s2m_nn.release();
+  c->sc_cloud.release(); c->sc_bins.release(); c->sc_out.release();
   c->corr.release(); c->partials.release(); c->counter.release(); c->result_dev.release(); c->st_dev.release(); c->staging.release(); c->sched_dev.release();
   for (int p = 0; p < XCHG_MAX_RANKS; p++) if (c->peer_xchg[p] && c->peer_xchg[p] != c->xchg) cudaIpcCloseMemHandle(c->peer_xchg[p]);
   if (c->xchg) cudaFree(c->xchg);
@@ -1673,5 +1681,70 @@ extern "C" int rg_s2m_optimize(rg_ctx* c, float tf[6], int max_iterations, int e
     if ((double)deltaR < 0.05 && (double)deltaT < 0.05) { out->converged = 1; break; }
   }
   out->degenerate = degenerate ? 1 : 0;
+  return RG_OK;
+}
+
+// ---- Scan Context place recognition (src/scancontext/Scancontext.cpp) ------------------------------
+
+extern "C" int rg_sc_make_and_save(rg_ctx* c, const float* pts, size_t n, size_t stride_bytes, double lidar_height) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (int rc = upload_cloud(c, c->sc_cloud, pts, n, stride_bytes)) return rc;
+  RG_CUDA(c, c->sc_bins.ensure(c->device, SC_BINS));
+  RG_CUDA(c, c->sc_out.ensure(c->device, SC_BINS + SC_NUM_RING + SC_NUM_SECTOR));
+  SCLaunch L;
+  L.pts = c->sc_cloud.pts.p; L.n = (int)n; L.lidar_height = lidar_height; L.max_radius = 80.0;   // PC_MAX_RADIUS (Scancontext.h:84)
+  L.bins = c->sc_bins.p; L.desc = c->sc_out.p; L.ring_key = c->sc_out.p + SC_BINS; L.sector_key = c->sc_out.p + SC_BINS + SC_NUM_RING;
+  RG_CUDA(c, launch_scancontext(L, c->stream));
+  g_launches += 3;
+  double h[SC_BINS + SC_NUM_RING + SC_NUM_SECTOR];
+  RG_CUDA(c, cudaMemcpyAsync(h, c->sc_out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  sc::Entry e;
+  std::memcpy(e.desc, h, sizeof(e.desc)); std::memcpy(e.ring_key, h + SC_BINS, sizeof(e.ring_key)); std::memcpy(e.sector_key, h + SC_BINS + SC_NUM_RING, sizeof(e.sector_key));
+  for (int k = 0; k < SC_NUM_RING; k++) e.ring_key_f[k] = (float)e.ring_key[k];      // eig2stdvec (Scancontext.cpp:62-66)
+  c->sc_mgr.entries.push_back(e);
+  return RG_OK;
+}
+
+extern "C" int rg_sc_size(rg_ctx* c) { return c ? (int)c->sc_mgr.entries.size() : 0; }
+
+extern "C" int rg_sc_clear(rg_ctx* c) {
+  CHECK_CTX(c);
+  c->sc_mgr = sc::Manager();
+  return RG_OK;
+}
+
+static const sc::Entry* sc_entry(rg_ctx* c, int index) {
+  const int n = (int)c->sc_mgr.entries.size();
+  if (index < 0) index += n;
+  return (index >= 0 && index < n) ? &c->sc_mgr.entries[index] : nullptr;
+}
+
+extern "C" int rg_sc_get(rg_ctx* c, int index, double* desc, double* ring_key, double* sector_key) {
+  CHECK_CTX(c);
+  const sc::Entry* e = sc_entry(c, index);
+  if (!e) return set_err(c, RG_ERR_INVALID, "rg_sc_get: no such descriptor");
+  if (desc) std::memcpy(desc, e->desc, sizeof(e->desc));
+  if (ring_key) std::memcpy(ring_key, e->ring_key, sizeof(e->ring_key));
+  if (sector_key) std::memcpy(sector_key, e->sector_key, sizeof(e->sector_key));
+  return RG_OK;
+}
+
+extern "C" int rg_sc_distance(rg_ctx* c, int i, int j, double* dist, int32_t* shift) {
+  CHECK_CTX(c);
+  const sc::Entry *a = sc_entry(c, i), *b = sc_entry(c, j);
+  if (!a || !b || !dist || !shift) return set_err(c, RG_ERR_INVALID, "rg_sc_distance: bad arguments");
+  const std::pair<double, int> r = sc::distance(*a, *b);
+  *dist = r.first; *shift = r.second;
+  return RG_OK;
+}
+
+extern "C" int rg_sc_detect(rg_ctx* c, int32_t* loop_id, float* yaw_diff_rad) {
+  CHECK_CTX(c);
+  if (!loop_id || !yaw_diff_rad) return set_err(c, RG_ERR_INVALID, "rg_sc_detect: null argument");
+  if (c->sc_mgr.entries.empty()) return set_err(c, RG_ERR_INVALID, "rg_sc_detect: no descriptor saved yet");
+  const std::pair<int, float> r = c->sc_mgr.detect();
+  *loop_id = r.first; *yaw_diff_rad = r.second;
   return RG_OK;
 }
