@@ -279,6 +279,17 @@ int rg_sc_get(rg_ctx*, int index, double* desc1200, double* ring_key20, double* 
 int rg_sc_distance(rg_ctx*, int i, int j, double* dist, int32_t* shift);
 int rg_sc_detect(rg_ctx*, int32_t* loop_id, float* yaw_diff_rad);
 
+/* ---- loop-closure verification (src/backMapping.cpp:2331-2352,2408-2431) -------------------------------
+ * The reference aligns the current keyframe cloud to the candidate's with pcl::IterativeClosestPoint and accepts the loop when
+ * hasConverged() && getFitnessScore() <= historyKeyframeFitnessScore. With this library the alignment is the GICP core in its
+ * 6-DoF LM mode (rg_set_optimizer_type(RG_OPT_LM) + rg_align on the two keyframe clouds) and the acceptance test is
+ *   rg_get_fitness_score = pcl::Registration::getFitnessScore(max_range): mean of the squared distances from every source
+ *   point, moved by T, to its exact nearest target point, over the pairs with squared distance <= max_range (the reference
+ *   compares the SQUARED distance with max_range; default DBL_MAX); DBL_MAX when no pair qualifies.
+ *   rg_nearest_target = the per-point result behind it: target index int32[n_source], squared distance float[n_source]. */
+int rg_get_fitness_score(rg_ctx*, const float T[16], double max_range, double* score);
+int rg_nearest_target(rg_ctx*, const float T[16], int32_t* idx, float* sq_dist);
+
 #ifdef __cplusplus
 }
 #endif

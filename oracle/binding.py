@@ -191,6 +191,16 @@ class Oracle:
     def getFinalPoseDouble(self):
         T = np.empty((4, 4)); self.L.ro_get_final_pose_d(self.h, _d(T)); return T
 
+    def getFitnessScore(self, T, max_range=float(np.finfo(np.float64).max), n_source=None):
+        """pcl::Registration::getFitnessScore(max_range); with n_source also returns (idx, d2) per source point."""
+        self.L.ro_get_fitness_score.restype = C.c_double
+        t = np.ascontiguousarray(T, dtype=np.float32).reshape(16)
+        if n_source is None:
+            return self.L.ro_get_fitness_score(self.h, C.c_void_p(t.ctypes.data), C.c_double(max_range), None, None)
+        idx = np.empty(n_source, np.int32); d2 = np.empty(n_source, np.float32)
+        sc = self.L.ro_get_fitness_score(self.h, C.c_void_p(t.ctypes.data), C.c_double(max_range), C.c_void_p(idx.ctypes.data), C.c_void_p(d2.ctypes.data))
+        return sc, idx, d2
+
     def hasConverged(self): return bool(self.L.ro_has_converged(self.h))
     def nrIterations(self): return self.L.ro_nr_iterations(self.h)
 

@@ -975,6 +975,26 @@ int ro_align(ro_ctx* c, const float guess[16], float out_T[16]) { return c->alig
 int ro_compute_translation(ro_ctx* c, double trans[3], const double g[3], const double l[3], double dtn, double dtn1, float lam) {
   return c->compute_translation(trans, g, l, dtn, dtn1, lam);
 }
+/* pcl::Registration::getFitnessScore(max_range) (PCL registration.hpp; not in /root/reference): every source point is moved by
+ * T (float, ((a x + b y) + c z) + d), its nearest target point is searched (float squared distance, ties by index), and the
+ * squared distances <= max_range are averaged in double, in point order. idx / d2 (optional) receive the per-point result. */
+double ro_get_fitness_score(ro_ctx* c, const float T[16], double max_range, int* idx, float* d2) {
+  const int n = (int)(c->source.size() / 4);
+  KdTree tree; tree.build(c->target.data(), (int)(c->target.size() / 4));
+  std::vector<int> id(n, -1); std::vector<float> dd(n, 0.f);
+#pragma omp parallel for num_threads(c->num_threads) schedule(guided, 8)
+  for (int i = 0; i < n; i++) {
+    const float x = c->source[i*4], y = c->source[i*4+1], z = c->source[i*4+2];
+    const float q[3] = {((T[0]*x + T[1]*y) + T[2]*z) + T[3], ((T[4]*x + T[5]*y) + T[6]*z) + T[7], ((T[8]*x + T[9]*y) + T[10]*z) + T[11]};
+    int j; float d;
+    if (tree.knn_dist(q, 1, &j, &d) == 1) { id[i] = j; dd[i] = d; } else { dd[i] = INFINITY; }
+  }
+  double fitness = 0.0; int nr = 0;
+  for (int i = 0; i < n; i++) if ((double)dd[i] <= max_range) { fitness += (double)dd[i]; nr++; }
+  if (idx) std::memcpy(idx, id.data(), sizeof(int) * n);
+  if (d2) std::memcpy(d2, dd.data(), sizeof(float) * n);
+  return nr > 0 ? fitness / nr : std::numeric_limits<double>::max();
+}
 int ro_has_converged(ro_ctx* c) { return c->converged ? 1 : 0; }
 int ro_nr_iterations(ro_ctx* c) { return c->nr_iterations; }
 void ro_get_final_hessian(ro_ctx* c, double* H) { std::memcpy(H, c->final_hessian, 36 * sizeof(double)); }

@@ -86,6 +86,8 @@ void   ro_get_correspondences(ro_ctx*, int* src_idx, int* vox_key);
 int  ro_align(ro_ctx*, const float guess[16], float out_T[16]);
 int  ro_compute_translation(ro_ctx*, double trans[3] /*inout*/, const double guess[3], const double last_t0[3],
                             double dtn, double dtn1, float ct_lambda);
+/* pcl::Registration::getFitnessScore(max_range) at transform T (row-major 4x4 float); idx int[n_source] / d2 float[n_source] optional */
+double ro_get_fitness_score(ro_ctx*, const float T[16], double max_range, int* idx, float* d2);
 int  ro_has_converged(ro_ctx*);
 int  ro_nr_iterations(ro_ctx*);
 void ro_get_final_hessian(ro_ctx*, double* H36);

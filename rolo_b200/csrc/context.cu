@@ -280,6 +280,11 @@ struct rg_ctx {
   DevBuf<double> s2m_partial, s2m_result;
   DevBuf<unsigned> s2m_counter;
   DevBuf<int> s2m_nn;
+  // getFitnessScore: Morton index of the target + per-source-point nearest neighbour
+  DevBuf<float4> fit_sorted;
+  DevBuf<unsigned long long> fit_codes;
+  DevBuf<int> fit_bucket, fit_bbox, fit_idx;
+  DevBuf<float> fit_d2, fit_T;
   // Scan Context place recognition (src/scancontext/Scancontext.cpp): descriptor kernel + host manager
   Cloud sc_cloud;
   DevBuf<int> sc_bins;
@@ -727,6 +732,7 @@ void rg_destroy(rg_ctx* c) {
   for (int k = 0; k < 2; k++) { c->s2m_sorted[k].release(); c->s2m_coeff[k].release(); c->s2m_codes[k].release(); c->s2m_bucket[k].release(); c->s2m_bbox[k].release(); c->s2m_flag[k].release(); }
   c->s2m_partial.release(); c->s2m_result.release(); c->s2m_counter.release(); c->s2m_nn.release();
   c->sc_cloud.release(); c->sc_bins.release(); c->sc_out.release();
+  c->fit_sorted.release(); c->fit_codes.release(); c->fit_bucket.release(); c->fit_bbox.release(); c->fit_idx.release(); c->fit_d2.release(); c->fit_T.release();
   c->corr.release(); c->partials.release(); c->counter.release(); c->result_dev.release(); c->st_dev.release(); c->staging.release(); c->sched_dev.release();
   for (int p = 0; p < XCHG_MAX_RANKS; p++) if (c->peer_xchg[p] && c->peer_xchg[p] != c->xchg) cudaIpcCloseMemHandle(c->peer_xchg[p]);
   if (c->xchg) cudaFree(c->xchg);
@@ -1746,5 +1752,53 @@ extern "C" int rg_sc_detect(rg_ctx* c, int32_t* loop_id, float* yaw_diff_rad) {
   if (c->sc_mgr.entries.empty()) return set_err(c, RG_ERR_INVALID, "rg_sc_detect: no descriptor saved yet");
   const std::pair<int, float> r = c->sc_mgr.detect();
   *loop_id = r.first; *yaw_diff_rad = r.second;
+  return RG_OK;
+}
+
+// ---- pcl::Registration::getFitnessScore / loop-closure verification (backMapping.cpp:2351,2428) -------
+
+// nearest target point of every source point moved by T (row-major 4x4 float)
+static int nearest_target(rg_ctx* c, const float T[16]) {
+  if (c->src.n == 0 || c->tgt.n == 0) return set_err(c, RG_ERR_INVALID, "fitness score: source and target clouds must be set");
+  const int n = c->tgt.n, nq = c->src.n;
+  RG_CUDA(c, c->codes_in.ensure(c->device, n)); RG_CUDA(c, c->idx_in.ensure(c->device, n)); RG_CUDA(c, c->idx_out.ensure(c->device, n));
+  RG_CUDA(c, c->fit_codes.ensure(c->device, n)); RG_CUDA(c, c->fit_sorted.ensure(c->device, n));
+  RG_CUDA(c, c->fit_bbox.ensure(c->device, 8)); RG_CUDA(c, c->fit_bucket.ensure(c->device, cov_bucket_table_entries()));
+  const size_t tb = cov_cub_temp_bytes(n);
+  RG_CUDA(c, c->cub_temp.ensure(c->device, tb));
+  RG_CUDA(c, c->fit_idx.ensure(c->device, nq)); RG_CUDA(c, c->fit_d2.ensure(c->device, nq)); RG_CUDA(c, c->fit_T.ensure(c->device, 12));
+  CovScratch sc;
+  sc.codes_in = c->codes_in.p; sc.codes_out = c->fit_codes.p; sc.idx_in = c->idx_in.p; sc.idx_out = c->idx_out.p; sc.sorted = c->fit_sorted.p;
+  sc.cub_temp = c->cub_temp.p; sc.cub_temp_bytes = tb; sc.bbox = c->fit_bbox.p; sc.bucket_start = c->fit_bucket.p;
+  RG_CUDA(c, launch_sort_cloud(c->tgt.pts.p, n, sc, true, c->stream));          // tree_->setInputCloud(target_) of pcl::Registration
+  RG_CUDA(c, cudaMemcpyAsync(c->fit_T.p, T, 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  RG_CUDA(c, launch_nearest(c->src.pts.p, nq, c->fit_T.p, sc, n, c->fit_idx.p, c->fit_d2.p, c->stream));
+  g_launches += 6;
+  return RG_OK;
+}
+
+extern "C" int rg_nearest_target(rg_ctx* c, const float T[16], int32_t* idx, float* sq_dist) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (!T) return set_err(c, RG_ERR_INVALID, "rg_nearest_target: null transform");
+  if (int rc = nearest_target(c, T)) return rc;
+  if (idx) RG_CUDA(c, cudaMemcpyAsync(idx, c->fit_idx.p, sizeof(int) * (size_t)c->src.n, cudaMemcpyDeviceToHost, c->stream));
+  if (sq_dist) RG_CUDA(c, cudaMemcpyAsync(sq_dist, c->fit_d2.p, sizeof(float) * (size_t)c->src.n, cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return RG_OK;
+}
+
+extern "C" int rg_get_fitness_score(rg_ctx* c, const float T[16], double max_range, double* score) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (!T || !score) return set_err(c, RG_ERR_INVALID, "rg_get_fitness_score: null argument");
+  if (int rc = nearest_target(c, T)) return rc;
+  std::vector<float> d2((size_t)c->src.n);
+  RG_CUDA(c, cudaMemcpyAsync(d2.data(), c->fit_d2.p, sizeof(float) * d2.size(), cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  // the reference's accumulation: doubles, in point order, squared distance compared with max_range as is
+  double fitness = 0.0; int nr = 0;
+  for (float d : d2) if ((double)d <= max_range) { fitness += (double)d; nr++; }
+  *score = nr > 0 ? fitness / nr : 1.7976931348623157e308;
   return RG_OK;
 }

@@ -20,6 +20,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <float.h>
+#include <math_constants.h>
 #include <limits.h>
 
 namespace rolo {
@@ -347,6 +348,105 @@ knn_warp_kernel(const float4* __restrict__ sorted, const unsigned long long* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// exact nearest neighbour of EXTERNAL query points (pcl::Registration::getFitnessScore's nearestKSearch(1) over the target),
+// one warp per query. The query is optionally moved by a 3x4 float transform first (row-major; ((a x + b y) + c z) + d with
+// every operation rounded, like the oracle). Start level: the insertion position of the query's Morton code among the sorted
+// codes gives, through the common prefix with its two neighbours, the finest level at which the query's cell is occupied;
+// the 3x3x3 block there is scanned (lane-wise minimum, one warp reduction), the result is exact once the distance is inside
+// the radius the block covers, otherwise one level coarser. Queries outside the bounding box are clamped for the cell
+// lookup; the coverage test uses their true coordinates, so they stay exact (and cost more the farther away they are).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+nn1_warp_kernel(const float4* __restrict__ queries, int nq, const float* __restrict__ T12, const float4* __restrict__ sorted,
+                const unsigned long long* __restrict__ codes, const int* __restrict__ bucket_start, int n, const int* __restrict__ bbox,
+                int* __restrict__ out_idx, float* __restrict__ out_d2) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int j = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (j >= nq) return;
+  const Quant qn = make_quant(bbox);
+  float4 q = __ldg(queries + j);
+  if (T12) {
+    const float x = q.x, y = q.y, z = q.z;
+    q.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T12[0], x), __fmul_rn(T12[1], y)), __fmul_rn(T12[2], z)), T12[3]);
+    q.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T12[4], x), __fmul_rn(T12[5], y)), __fmul_rn(T12[6], z)), T12[7]);
+    q.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T12[8], x), __fmul_rn(T12[9], y)), __fmul_rn(T12[10], z)), T12[11]);
+  }
+  unsigned ix, iy, iz;
+  quantize(qn, q.x, q.y, q.z, ix, iy, iz);
+  const unsigned long long cq = morton3(ix, iy, iz);
+  const int pos = lower_bound_bucketed(codes, bucket_start, cq);
+  const unsigned long long xl = pos > 0 ? (cq ^ __ldg(codes + pos - 1)) : ~0ull, xr = pos < n ? (cq ^ __ldg(codes + pos)) : ~0ull;
+  const int bl = pos > 0 ? (xl ? (__clzll((long long)xl) - (64 - CODE_BITS)) : CODE_BITS) : 0;
+  const int br = pos < n ? (xr ? (__clzll((long long)xr) - (64 - CODE_BITS)) : CODE_BITS) : 0;
+  int L = min(max(bl, br) / 3, MORTON_BITS);
+  const double rel[3] = {(double)q.x - qn.mn[0], (double)q.y - qn.mn[1], (double)q.z - qn.mn[2]};
+  unsigned long long best = KEY_INF;
+  #pragma unroll 1
+  for (;; L--) {
+    const int sh = MORTON_BITS - L;
+    const int cx = (int)(ix >> sh), cy = (int)(iy >> sh), cz = (int)(iz >> sh);
+    const int ncell = 1 << L;
+    int lo = 0, cnt = 0;
+    if (lane < 27) {
+      const int nx = cx + lane % 3 - 1, ny = cy + (lane / 3) % 3 - 1, nz = cz + lane / 9 - 1;
+      if (nx >= 0 && ny >= 0 && nz >= 0 && nx < ncell && ny < ncell && nz < ncell) {
+        const unsigned long long pre = morton3((unsigned)nx, (unsigned)ny, (unsigned)nz);
+        lo = lower_bound_bucketed(codes, bucket_start, pre << (3 * sh));
+        const int hi = (L == 0) ? n : lower_bound_bucketed(codes, bucket_start, (pre + 1ull) << (3 * sh));
+        cnt = hi - lo;
+      }
+    }
+    int incl = cnt;
+    #pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    const int excl = incl - cnt;
+    best = KEY_INF;
+    #pragma unroll 1
+    for (int base = 0; base < total; base += 32) {
+      const int g = base + lane;
+      int a = 0, b = 26;
+      #pragma unroll
+      for (int s = 0; s < 5; s++) {
+        const int mid = (a + b) >> 1;
+        const int v = __shfl_sync(FULL, incl, mid);
+        if (v <= g) a = mid + 1; else b = mid;
+      }
+      a = min(a, 26);
+      const int cell_lo = __shfl_sync(FULL, lo, a), cell_ex = __shfl_sync(FULL, excl, a);
+      if (g < total) {
+        const float4 p = __ldg(sorted + cell_lo + (g - cell_ex));
+        const float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
+        float d = __fmul_rn(dx, dx);
+        d = __fadd_rn(d, __fmul_rn(dy, dy));
+        d = __fadd_rn(d, __fmul_rn(dz, dz));
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+        if (key < best) best = key;
+      }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(FULL, best, o); if (other < best) best = other; }
+    if (L == 0) break;
+    if (best != KEY_INF) {
+      const double sL = qn.cell * (double)(1 << sh);
+      double rs = 1e300;
+      const int cc[3] = {cx, cy, cz};
+      #pragma unroll
+      for (int dd = 0; dd < 3; dd++) {
+        if (cc[dd] - 1 >= 0) rs = fmin(rs, rel[dd] - (double)(cc[dd] - 1) * sL);
+        if (cc[dd] + 1 < ncell) rs = fmin(rs, (double)(cc[dd] + 2) * sL - rel[dd]);
+      }
+      if (rs > 0.0 && (double)__uint_as_float((unsigned)(best >> 32)) <= rs * rs * (1.0 - 1e-6)) break;
+    }
+  }
+  if (lane == 0) {
+    out_idx[j] = best == KEY_INF ? -1 : (int)(unsigned)(best & 0xFFFFFFFFull);
+    out_d2[j] = best == KEY_INF ? CUDART_INF_F : __uint_as_float((unsigned)(best >> 32));
+  }
+}
+
 // generic fallback (32 < k <= 64): one thread per query, local-memory top-k
 __global__ void __launch_bounds__(128)
 knn_thread_kernel(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes, int n, int k,
@@ -454,6 +554,13 @@ cudaError_t launch_sort_cloud(const float4* pts, int n, const CovScratch& s, boo
   if (e != cudaSuccess) return e;
   gather_sorted_kernel<<<nb, tb, 0, stream>>>(pts, s.idx_out, n, s.sorted);
   if (bucket_table) bucket_table_kernel<<<(N_BUCKETS + 1 + tb - 1) / tb, tb, 0, stream>>>(s.codes_out, n, s.bucket_start);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nearest(const float4* queries, int nq, const float* T12_dev, const CovScratch& s, int n, int* out_idx, float* out_d2, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  if (n <= 0) return cudaErrorInvalidValue;
+  nn1_warp_kernel<<<(unsigned)(((long long)nq * 32 + 255) / 256), 256, 0, stream>>>(queries, nq, T12_dev, s.sorted, s.codes_out, s.bucket_start, n, s.bbox, out_idx, out_d2);
   return cudaGetLastError();
 }
 

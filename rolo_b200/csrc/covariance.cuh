@@ -31,6 +31,9 @@ struct CovLaunch {
 
 cudaError_t launch_covariances(const CovLaunch& L, cudaStream_t stream);
 // spatial index only (bbox, Morton codes, sort, Morton-ordered copy, optional bucket table)
+// exact nearest indexed point (original numbering) + float squared distance of every query (optionally moved by the device-resident
+// 3x4 row-major float transform T12_dev first); `s` must hold the index launch_sort_cloud(…, bucket_table = true) built over n points
+cudaError_t launch_nearest(const float4* queries, int nq, const float* T12_dev, const CovScratch& s, int n, int* out_idx, float* out_d2, cudaStream_t stream);
 cudaError_t launch_sort_cloud(const float4* pts, int n, const CovScratch& s, bool bucket_table, cudaStream_t stream);
 
 }  // namespace rolo

@@ -268,6 +268,20 @@ class RotVGICP:
         self._keep[which] = None
         return nc.value, ns.value
 
+    def getFitnessScore(self, T=None, max_range: float = float(np.finfo(np.float64).max)) -> float:
+        """pcl::Registration::getFitnessScore(max_range) at transform T (default: the final transformation of the last align)."""
+        T = self._final if T is None else T
+        t = np.ascontiguousarray(T, dtype=np.float32).reshape(16)
+        s = C.c_double()
+        self._ck(self._L.rg_get_fitness_score(self._h, t.ctypes.data_as(capi.fp), max_range, C.byref(s)))
+        return s.value
+
+    def nearestTarget(self, T, n_source: int):
+        t = np.ascontiguousarray(T, dtype=np.float32).reshape(16)
+        idx = np.empty(n_source, np.int32); d2 = np.empty(n_source, np.float32)
+        self._ck(self._L.rg_nearest_target(self._h, t.ctypes.data_as(capi.fp), C.c_void_p(idx.ctypes.data), C.c_void_p(d2.ctypes.data)))
+        return idx, d2
+
     def setSourceShard(self, lo: int, hi: int): self._ck(self._L.rg_set_source_shard(self._h, lo, hi))
 
     def shardExport(self) -> bytes:
