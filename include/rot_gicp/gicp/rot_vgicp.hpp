@@ -22,6 +22,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <limits>
 #include <vector>
 
 #include <Eigen/Core>
@@ -90,6 +91,16 @@ public:
   void setDebugPrint(bool on) { check(rg_set_debug_print(ctx_, on ? 1 : 0), "setDebugPrint"); }
   void setOptimizerType(LSQ_OPTIMIZER_TYPE t) { check(rg_set_optimizer_type(ctx_, static_cast<int>(t)), "setOptimizerType"); }
   const Eigen::Matrix<double, 6, 6>& getFinalHessian() const { return final_hessian_; }
+
+  // pcl::Registration::getFitnessScore(max_range) (used by the loop-closure check, backMapping.cpp:2351,2428): mean squared
+  // distance source -> nearest target under final_transformation_, on the device (rg_get_fitness_score)
+  double getFitnessScore(double max_range = std::numeric_limits<double>::max()) {
+    float Tr[16];
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) Tr[i * 4 + j] = final_transformation_(i, j);
+    double score = 0.0;
+    check(rg_get_fitness_score(ctx_, Tr, max_range, &score), "getFitnessScore");
+    return score;
+  }
 
   double evaluateCost(const Eigen::Matrix4f& relative_pose, Eigen::Matrix<double, 6, 6>* H = nullptr, Eigen::Matrix<double, 6, 1>* b = nullptr) {
     double T[16], Hr[36], br[6], cost = 0.0;

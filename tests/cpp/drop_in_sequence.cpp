@@ -53,6 +53,8 @@ int main(int argc, char** argv) {
   std::printf("converged=%d R0=[% .6f % .6f % .6f] t=[% .6f % .6f % .6f] aligned=%zu first=[% .5f % .5f % .5f]\n", (int)rot_vgicp.hasConverged(),
               trans(0, 0), trans(0, 1), trans(0, 2), Reg_translation(0), Reg_translation(1), Reg_translation(2), aligned->size(),
               aligned->points[0].x, aligned->points[0].y, aligned->points[0].z);
+  // loop-closure style acceptance value (backMapping.cpp:2351): pcl::Registration::getFitnessScore()
+  std::printf("fitness=%.12e\n", rot_vgicp.getFitnessScore());
   // the aliasing check of rot_vgicp_impl.hpp:150-152 must throw std::invalid_argument
   try { pcl::PointCloud<PointType>& alias = const_cast<pcl::PointCloud<PointType>&>(*feature_propagated); rot_vgicp.align(alias); std::printf("alias=NOTHROW\n"); }
   catch (const std::invalid_argument&) { std::printf("alias=invalid_argument\n"); }
