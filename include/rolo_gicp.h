@@ -27,6 +27,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden: only this ABI is exported */
+#endif
 
 #define ROLO_GICP_ABI_VERSION 1
 
@@ -290,6 +293,9 @@ int rg_sc_detect(rg_ctx*, int32_t* loop_id, float* yaw_diff_rad);
 int rg_get_fitness_score(rg_ctx*, const float T[16], double max_range, double* score);
 int rg_nearest_target(rg_ctx*, const float T[16], int32_t* idx, float* sq_dist);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

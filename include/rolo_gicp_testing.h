@@ -8,6 +8,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden: only this ABI is exported */
+#endif
 
 typedef struct rgt_lsq rgt_lsq;   /* one host::LsqDriver */
 enum { RGT_REQ_NONE = 0, RGT_REQ_LIN6, RGT_REQ_LIN3, RGT_REQ_ERROR, RGT_REQ_T3_LIN, RGT_REQ_T_ERROR };
@@ -35,6 +38,9 @@ void rgt_s2m_qr_solve(int rows, int cols /* 5x3 pivoted or 6x6 */, const float* 
 int  rgt_s2m_invert6(const float* A, float* inv);
 void rgt_s2m_get_transformation(const float tf[6], float t12[12]);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

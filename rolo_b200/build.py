@@ -20,10 +20,10 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-ccbin", HOST_CXX, "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-fvisibility=hidden",
           "--expt-relaxed-constexpr", "-Xptxas", "-v", "-I", os.path.join(HERE, "..", "include")]
 EXTRA = os.environ.get("ROLO_NVCC_FLAGS", "").split()
-SOURCES = ["linearize.cu", "voxelmap.cu", "covariance.cu", "frontend.cu", "scan2map.cu", "scancontext.cu", "context.cu", "testing_hooks.cu"]
+SOURCES = ["linearize.cu", "voxelmap.cu", "covariance.cu", "frontend.cu", "scan2map.cu", "scancontext.cu", "context.cu", "abi_frontend.cu", "abi_mapping.cu", "testing_hooks.cu"]
 # scan2map.cu restates float arithmetic of the reference operation by operation: no FMA contraction there
 PER_FILE = {"scan2map.cu": ["-fmad=false"]}
 

@@ -1,127 +1,19 @@
-// context.cu — registration context, device-memory pool, host drivers and the C-ABI (include/rolo_gicp.h).
+// context.cu — registration context, device-memory pool, host drivers and the registration part of the C-ABI
+// (include/rolo_gicp.h); the front-end and mapping entry points live in abi_frontend.cu / abi_mapping.cu over context.hpp.
 //
 // The product path is CUDA-only: every entry point fails with RG_ERR_NO_DEVICE / RG_ERR_CUDA when no
 // B200-class device is usable; there is no CPU fallback anywhere in this library.
 
-#include <atomic>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <chrono>
-#include <map>
-#include <mutex>
-#include <string>
-#include <vector>
-#include <algorithm>
+#include "context.hpp"
 
-#include "../../include/rolo_gicp.h"
-#include "common.cuh"
-#include "covariance.cuh"
-#include "frontend.cuh"
-#include "linearize.cuh"
-#include "lsq_host.hpp"
-#include "cloud_info.hpp"
-#include "scan2map.cuh"
-#include "scancontext.cuh"
-#include "sc_host.hpp"
-#include "s2m_math.cuh"
-#include "voxelmap.cuh"
-
-using namespace rolo;
+std::mutex g_mutex;
+std::atomic<unsigned long long> g_launches{0};
+Pool& pool() { static Pool* p = new Pool; return *p; }   // intentionally leaked: safe at process exit
 
 namespace {
 
-std::mutex g_mutex;
 std::string g_last_error;
-std::atomic<unsigned long long> g_launches{0};   // own kernels launched (bench.py's gpu_launches claim)
 std::atomic<unsigned> g_seq{0};   // launch sequence numbers written to the mapped completion flags
-
-// ------------------------------------------------------------------------------------------------
-// process-global caching pool: the caller constructs a fresh registration object every frame
-// (lidarOdometry.cpp:460), so device buffers, pinned blocks and streams must outlive contexts.
-// ------------------------------------------------------------------------------------------------
-struct Pool {
-  std::multimap<std::pair<int, size_t>, void*> free_dev;    // (device, bytes) -> ptr
-  std::multimap<size_t, void*> free_pinned;
-  std::multimap<int, cudaStream_t> free_streams;
-  std::map<void*, std::pair<int, size_t>> live_dev;
-  std::map<void*, size_t> live_pinned;
-
-  static size_t round_up(size_t b) {
-    size_t g = 256;
-    while (g < b) g <<= 1;
-    if (b > (size_t)1 << 20) { const size_t q = (size_t)1 << 20; g = (b + q - 1) / q * q; }
-    return g;
-  }
-  cudaError_t dev_alloc(int device, size_t bytes, void** out) {
-    bytes = round_up(std::max<size_t>(bytes, 256));
-    std::lock_guard<std::mutex> lk(g_mutex);
-    auto it = free_dev.find({device, bytes});
-    if (it != free_dev.end()) { *out = it->second; free_dev.erase(it); live_dev[*out] = {device, bytes}; return cudaSuccess; }
-    cudaError_t e = cudaMalloc(out, bytes);
-    if (e != cudaSuccess) {   // release cached blocks and retry once
-      for (auto& kv : free_dev) cudaFree(kv.second);
-      free_dev.clear();
-      e = cudaMalloc(out, bytes);
-      if (e != cudaSuccess) return e;
-    }
-    live_dev[*out] = {device, bytes};
-    return cudaSuccess;
-  }
-  void dev_free(void* p) {
-    if (!p) return;
-    std::lock_guard<std::mutex> lk(g_mutex);
-    auto it = live_dev.find(p);
-    if (it == live_dev.end()) return;
-    free_dev.insert({it->second, p});
-    live_dev.erase(it);
-  }
-  cudaError_t pinned_alloc(size_t bytes, void** out) {
-    bytes = round_up(std::max<size_t>(bytes, 256));
-    std::lock_guard<std::mutex> lk(g_mutex);
-    auto it = free_pinned.find(bytes);
-    if (it != free_pinned.end()) { *out = it->second; free_pinned.erase(it); live_pinned[*out] = bytes; return cudaSuccess; }
-    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
-    if (e != cudaSuccess) return e;
-    live_pinned[*out] = bytes;
-    return cudaSuccess;
-  }
-  void pinned_free(void* p) {
-    if (!p) return;
-    std::lock_guard<std::mutex> lk(g_mutex);
-    auto it = live_pinned.find(p);
-    if (it == live_pinned.end()) return;
-    free_pinned.insert({it->second, p});
-    live_pinned.erase(it);
-  }
-  cudaError_t stream_get(int device, cudaStream_t* s) {
-    std::lock_guard<std::mutex> lk(g_mutex);
-    auto it = free_streams.find(device);
-    if (it != free_streams.end()) { *s = it->second; free_streams.erase(it); return cudaSuccess; }
-    return cudaStreamCreateWithFlags(s, cudaStreamNonBlocking);
-  }
-  void stream_put(int device, cudaStream_t s) {
-    std::lock_guard<std::mutex> lk(g_mutex);
-    free_streams.insert({device, s});
-  }
-};
-Pool& pool() { static Pool* p = new Pool; return *p; }   // intentionally leaked: safe at process exit
-
-template <typename T>
-struct DevBuf {
-  T* p = nullptr; size_t cap = 0; int device = 0;
-  cudaError_t ensure(int dev, size_t count) {
-    if (count <= cap && p) return cudaSuccess;
-    release();
-    device = dev;
-    void* q = nullptr;
-    cudaError_t e = pool().dev_alloc(dev, std::max<size_t>(count, 1) * sizeof(T), &q);
-    if (e != cudaSuccess) return e;
-    p = (T*)q; cap = count;
-    return cudaSuccess;
-  }
-  void release() { if (p) pool().dev_free(p); p = nullptr; cap = 0; }
-};
 
 __global__ void extract_points_kernel(const unsigned char* __restrict__ raw, size_t stride, int n, int n_pad, float4* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -184,154 +76,15 @@ __global__ void table_dump_kernel(const VoxSlot* __restrict__ table, unsigned ca
   out[sl.id] = vox[sl.id];
 }
 
-struct Cloud {
-  DevBuf<float4> pts;
-  DevBuf<float> cov6;
-  int n = 0, n_pad = 0;
-  bool has_cov = false;
-  const void* host_identity = nullptr;   // the reference compares cloud pointers (rot_vgicp_impl.hpp:113,134)
-  void clear() { n = 0; n_pad = 0; has_cov = false; host_identity = nullptr; }
-  void release() { pts.release(); cov6.release(); clear(); }
-};
-
 }  // namespace
 
-// ------------------------------------------------------------------------------------------------
-struct rg_ctx {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  bool own_stream = true;
-  cudaStream_t upload_stream = nullptr;   // H2D cloud uploads (== stream, or the pair's setup stream inside a batch)
-  cudaEvent_t ev_upload = nullptr;
-  bool side_pending = false;              // work queued on upload_stream that `stream` has not been ordered after yet
-  mutable std::string err;
-
-  // RotVGICP members (rot_vgicp_impl.hpp:20-39)
-  int k_correspondences = 20;
-  int regularization_method = RG_REG_PLANE;
-  double voxel_resolution = 1.0;
-  float lambda_ = 1.0f;
-  int search_method = RG_DIRECT1;
-  int voxel_mode = RG_ACC_ADDITIVE;
-  int voxel_type = RG_VOXEL_POLAR;
-  double polar_resolution[3] = {1.0, 0.0, 0.0};   // Vector3d::Identity() (reference quirk Q4: unusable until set)
-  int num_threads = 0;
-
-  host::LsqDriver lsq;
-
-  Cloud src, tgt;
-
-  // voxel map
-  DevBuf<VoxSlot> table; unsigned mask = 0;
-  DevBuf<VoxPayload> vox;
-  DevBuf<double> sums;
-  DevBuf<int> slot_of_point;
-  DevBuf<int> counters;
-  bool voxel_ok = false;
-  int n_vox = -1;
-
-  // covariance scratch
-  DevBuf<unsigned long long> codes_in, codes_out;
-  DevBuf<int> idx_in, idx_out, bbox;
-  DevBuf<float4> sorted;
-  DevBuf<unsigned char> cub_temp;
-  DevBuf<int> knn_idx, bucket_start;
-
-  // linearize
-  DevBuf<int> corr; int corr_noff = 0;
-  DevBuf<double> partials;
-  DevBuf<unsigned> counter;
-  DevBuf<double> result_dev;
-  DevBuf<LinStatic> st_dev; bool st_ok = false;
-  double* result_host = nullptr;        // mapped pinned [RES_N] (owned; stand-alone contexts)
-  unsigned* flag_host = nullptr;        // mapped pinned
-  double* result_view = nullptr;        // where the kernel writes this pair's result (own block or the batch's)
-  unsigned* flag_view = nullptr;
-  int lin_grid = 0, lin_tiles = 0;      // persistent-CTA grid and tile count of the stand-alone launch
-  DevBuf<int> sched_dev;
-  double R_lin[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-  bool have_corr = false;
-  size_t num_corr = 0;
-
-  DevBuf<unsigned char> staging;        // raw host cloud upload / misc
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool profile = false;
-  double last_kernel_us = -1.0;
-
-  rg_reduce_fn reduce_fn = nullptr; void* reduce_user = nullptr; int reduce_on_device = 0;
-  int shard_lo = 0, shard_hi = 0;       // evaluation range within the source cloud (0,0 = all)
-  // fused NVLink reduction (rg_shard_connect)
-  double* xchg = nullptr;               // own exchange buffer (plain cudaMalloc: exported through CUDA IPC)
-  double* peer_xchg[XCHG_MAX_RANKS] = {nullptr};
-  int p2p_rank = 0, p2p_world = 0;
-  unsigned shard_seq = 0;
-
-  // front end (range-image projection + feature extraction) scratch
-  DevBuf<unsigned char> fe_raw;
-  DevBuf<int> fe_owner, fe_row_count, fe_col, fe_start, fe_end, fe_counts, fe_picked, fe_label, fe_corner_cnt, fe_surf_cnt;
-  DevBuf<float> fe_range_image, fe_prange, fe_curv;
-  DevBuf<float4> fe_full, fe_extracted, fe_corner_ring, fe_surf_ring, fe_corner_out, fe_surf_out;
-  // scan-to-map optimisation (backMapping.cpp:681-1054): clouds 0/1 = corner/surface feature MAP, 2/3 = corner/surface SCAN
-  Cloud s2m_cloud[4];
-  DevBuf<float4> s2m_sorted[2], s2m_coeff[2];
-  DevBuf<unsigned long long> s2m_codes[2];
-  DevBuf<int> s2m_bucket[2], s2m_bbox[2];
-  DevBuf<unsigned char> s2m_flag[2];
-  DevBuf<double> s2m_partial, s2m_result;
-  DevBuf<unsigned> s2m_counter;
-  DevBuf<int> s2m_nn;
-  // getFitnessScore: Morton index of the target + per-source-point nearest neighbour
-  DevBuf<float4> fit_sorted;
-  DevBuf<unsigned long long> fit_codes;
-  DevBuf<int> fit_bucket, fit_bbox, fit_idx;
-  DevBuf<float> fit_d2, fit_T;
-  // Scan Context place recognition (src/scancontext/Scancontext.cpp): descriptor kernel + host manager
-  Cloud sc_cloud;
-  DevBuf<int> sc_bins;
-  DevBuf<double> sc_out;
-  sc::Manager sc_mgr;
-  bool s2m_map_ok = false, s2m_scan_ok = false, s2m_lin_ok = false;
-  DevBuf<unsigned char> fe_wire;        // packed PointXYZI records / uploaded message sections (cloud_info.hpp)
-  bool fe_frame_ok = false;             // rg_front_end_frame products are resident
-  int fe_n_scan = 0, fe_n[3] = {0, 0, 0};   // extracted, corner, surface counts of that frame
-
-  rg_batch* batch = nullptr;            // non-null when owned by a batch
-  int batch_index = 0;
-};
-
-struct rg_batch {
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  std::vector<rg_ctx*> pairs;
-  DevBuf<LinStatic> st_dev;
-  DevBuf<LinDyn> dyn_dev;
-  LinDyn* dyn_host = nullptr;           // pinned staging [P]
-  double* result_host = nullptr;        // mapped pinned [P][RES_N]
-  unsigned* flag_host = nullptr;        // mapped pinned [P]
-  std::vector<int> active;
-  DevBuf<LinStatic> st_sub; DevBuf<LinDyn> dyn_sub;
-  DevBuf<int> sched_dev; std::vector<int> sched_group; int sched_grid = 0, sched_tiles = 0;   // schedule of the last launched group
-  std::vector<cudaStream_t> setup_streams;   // covariance / voxel-map stages of different pairs overlap on these
-  std::vector<cudaEvent_t> setup_events;
-  cudaEvent_t ev_inputs = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  double lin_us_sum = 0; int lin_launches = 0;
-  std::string err;
-};
-
-namespace {
+// ---- helpers shared with abi_frontend.cu / abi_mapping.cu (declared in context.hpp) and local ones ----
 
 int set_err(const rg_ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg;
   { std::lock_guard<std::mutex> lk(g_mutex); g_last_error = msg; }
   return code;
 }
-#define RG_CUDA(ctx, expr)                                                                          \
-  do {                                                                                              \
-    cudaError_t _e = (expr);                                                                        \
-    if (_e != cudaSuccess)                                                                          \
-      return set_err(ctx, RG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
-  } while (0)
 
 int use_device(const rg_ctx* cc) {
   rg_ctx* c = const_cast<rg_ctx*>(cc);
@@ -668,7 +421,6 @@ int run_driver(rg_ctx* c, const double* g3, const double* l3, double dtn, double
   return RG_OK;
 }
 
-}  // namespace
 
 // ================================================================================================
 // C-ABI
@@ -744,7 +496,6 @@ void rg_destroy(rg_ctx* c) {
   delete c;
 }
 
-#define CHECK_CTX(c) do { if (!(c)) return set_err(nullptr, RG_ERR_INVALID, "null context"); } while (0)
 
 int rg_set_resolution(rg_ctx* c, double r) { CHECK_CTX(c); c->voxel_resolution = r; c->voxel_type = RG_VOXEL_UNIFORM; c->voxel_ok = false; c->st_ok = false; return RG_OK; }
 int rg_set_polar_resolution(rg_ctx* c, double th, double ph, double r) {
@@ -1266,539 +1017,4 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
   return rc_all;
 }
 
-// ------------------------------------------------------------------------------------------------
-// upstream range-image passes
-// ------------------------------------------------------------------------------------------------
-static int fe_alloc(rg_ctx* c, int n_scan, int horizon) {
-  const size_t cells = (size_t)n_scan * horizon;
-  RG_CUDA(c, c->fe_owner.ensure(c->device, cells)); RG_CUDA(c, c->fe_range_image.ensure(c->device, cells));
-  RG_CUDA(c, c->fe_full.ensure(c->device, cells)); RG_CUDA(c, c->fe_row_count.ensure(c->device, n_scan));
-  RG_CUDA(c, c->fe_extracted.ensure(c->device, cells)); RG_CUDA(c, c->fe_col.ensure(c->device, cells));
-  RG_CUDA(c, c->fe_prange.ensure(c->device, cells)); RG_CUDA(c, c->fe_start.ensure(c->device, n_scan)); RG_CUDA(c, c->fe_end.ensure(c->device, n_scan));
-  RG_CUDA(c, c->fe_counts.ensure(c->device, 8));
-  RG_CUDA(c, c->fe_curv.ensure(c->device, cells)); RG_CUDA(c, c->fe_picked.ensure(c->device, cells)); RG_CUDA(c, c->fe_label.ensure(c->device, cells));
-  RG_CUDA(c, c->fe_corner_ring.ensure(c->device, (size_t)n_scan * FE_MAX_CORNERS_PER_RING)); RG_CUDA(c, c->fe_corner_cnt.ensure(c->device, n_scan));
-  RG_CUDA(c, c->fe_surf_ring.ensure(c->device, cells)); RG_CUDA(c, c->fe_surf_cnt.ensure(c->device, n_scan));
-  RG_CUDA(c, c->fe_corner_out.ensure(c->device, (size_t)n_scan * FE_MAX_CORNERS_PER_RING)); RG_CUDA(c, c->fe_surf_out.ensure(c->device, cells));
-  return RG_OK;
-}
-
-int rg_image_projection(rg_ctx* c, const void* raw, size_t n_points, const rg_projection_params* p, float* range_image, float* extracted,
-                        int32_t* col_ind, float* point_range, int32_t* start_ring, int32_t* end_ring, int32_t* n_extracted) {
-  CHECK_CTX(c);
-  if (use_device(c)) return RG_ERR_CUDA;
-  if (!p || (!raw && n_points) || !n_extracted) return set_err(c, RG_ERR_INVALID, "rg_image_projection: null argument");
-  if (p->n_scan < 1 || p->horizon_scan < 1 || p->downsample_rate < 1 || p->point_stride_bytes < 12 || p->point_stride_bytes % 4 ||
-      p->ring_offset_bytes < 0 || p->ring_offset_bytes + 2 > p->point_stride_bytes || n_points > (size_t)INT32_MAX / 2)
-    return set_err(c, RG_ERR_INVALID, "rg_image_projection: bad parameters");
-  if (int rc = fe_alloc(c, p->n_scan, p->horizon_scan)) return rc;
-  const size_t cells = (size_t)p->n_scan * p->horizon_scan;
-  RG_CUDA(c, c->fe_raw.ensure(c->device, std::max<size_t>(n_points * p->point_stride_bytes, 16)));
-  if (n_points) RG_CUDA(c, cudaMemcpyAsync(c->fe_raw.p, raw, n_points * p->point_stride_bytes, cudaMemcpyHostToDevice, c->stream));
-  ProjLaunch L;
-  L.raw = c->fe_raw.p; L.n_points = (int)n_points; L.stride = p->point_stride_bytes; L.ring_offset = p->ring_offset_bytes;
-  L.n_scan = p->n_scan; L.horizon = p->horizon_scan; L.downsample = p->downsample_rate; L.min_range = p->lidar_min_range; L.max_range = p->lidar_max_range;
-  L.owner = c->fe_owner.p; L.range_image = c->fe_range_image.p; L.full = c->fe_full.p; L.row_count = c->fe_row_count.p;
-  L.extracted = c->fe_extracted.p; L.col_ind = c->fe_col.p; L.point_range = c->fe_prange.p; L.start_ring = c->fe_start.p; L.end_ring = c->fe_end.p;
-  L.n_extracted = c->fe_counts.p;
-  RG_CUDA(c, launch_projection(L, c->stream));
-  g_launches += 5;
-  int n = 0;
-  RG_CUDA(c, cudaMemcpyAsync(&n, c->fe_counts.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));
-  *n_extracted = n;
-  if (range_image) RG_CUDA(c, cudaMemcpyAsync(range_image, c->fe_range_image.p, cells * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  if (start_ring) RG_CUDA(c, cudaMemcpyAsync(start_ring, c->fe_start.p, p->n_scan * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  if (end_ring) RG_CUDA(c, cudaMemcpyAsync(end_ring, c->fe_end.p, p->n_scan * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  if (n > 0) {
-    if (extracted) RG_CUDA(c, cudaMemcpyAsync(extracted, c->fe_extracted.p, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-    if (col_ind) RG_CUDA(c, cudaMemcpyAsync(col_ind, c->fe_col.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    if (point_range) RG_CUDA(c, cudaMemcpyAsync(point_range, c->fe_prange.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  }
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));
-  return RG_OK;
-}
-
-int rg_feature_extraction(rg_ctx* c, const float* extracted, const int32_t* col_ind, const float* point_range, const int32_t* start_ring,
-                          const int32_t* end_ring, int32_t n, const rg_feature_params* p, float* curvature, int32_t* picked, int32_t* label,
-                          float* corner, int32_t* n_corner, float* surface, int32_t* n_surface) {
-  CHECK_CTX(c);
-  if (use_device(c)) return RG_ERR_CUDA;
-  if (!p || !extracted || !col_ind || !point_range || !start_ring || !end_ring || !n_corner || !n_surface)
-    return set_err(c, RG_ERR_INVALID, "rg_feature_extraction: null argument");
-  if (p->n_scan < 1 || p->horizon_scan < 1 || n < 1 || (size_t)n > (size_t)p->n_scan * p->horizon_scan || !(p->surf_leaf_size > 0.f))
-    return set_err(c, RG_ERR_INVALID, "rg_feature_extraction: bad parameters");
-  if (p->horizon_scan > FE_RING_CAP) return set_err(c, RG_ERR_UNSUPPORTED, "rg_feature_extraction: horizon_scan above the per-ring capacity (2048)");
-  if (int rc = fe_alloc(c, p->n_scan, p->horizon_scan)) return rc;
-  RG_CUDA(c, cudaMemcpyAsync(c->fe_extracted.p, extracted, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
-  RG_CUDA(c, cudaMemcpyAsync(c->fe_col.p, col_ind, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  RG_CUDA(c, cudaMemcpyAsync(c->fe_prange.p, point_range, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  RG_CUDA(c, cudaMemcpyAsync(c->fe_start.p, start_ring, p->n_scan * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  RG_CUDA(c, cudaMemcpyAsync(c->fe_end.p, end_ring, p->n_scan * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  RG_CUDA(c, cudaMemsetAsync(c->fe_counts.p, 0, 8 * sizeof(int), c->stream));
-  FeatLaunch L;
-  L.extracted = c->fe_extracted.p; L.col_ind = c->fe_col.p; L.point_range = c->fe_prange.p; L.start_ring = c->fe_start.p; L.end_ring = c->fe_end.p;
-  L.n_dev = nullptr; L.n = n; L.n_scan = p->n_scan; L.horizon = p->horizon_scan;
-  L.edge_thr = p->edge_threshold; L.surf_thr = p->surf_threshold; L.leaf = p->surf_leaf_size;
-  L.curvature = c->fe_curv.p; L.picked = c->fe_picked.p; L.label = c->fe_label.p;
-  L.corner_ring = c->fe_corner_ring.p; L.corner_cnt = c->fe_corner_cnt.p; L.surf_ring = c->fe_surf_ring.p; L.surf_cnt = c->fe_surf_cnt.p;
-  L.corner_out = c->fe_corner_out.p; L.n_corner = c->fe_counts.p + 1; L.surf_out = c->fe_surf_out.p; L.n_surf = c->fe_counts.p + 2;
-  L.error_flag = c->fe_counts.p + 3;
-  RG_CUDA(c, launch_features(L, c->stream));
-  g_launches += 5;
-  int h[4] = {0, 0, 0, 0};
-  RG_CUDA(c, cudaMemcpyAsync(h, c->fe_counts.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (h[3] != 0) return set_err(c, RG_ERR_UNSUPPORTED, "rg_feature_extraction: sector/ring capacity exceeded or inconsistent ring indices");
-  *n_corner = h[1]; *n_surface = h[2];
-  if (curvature) RG_CUDA(c, cudaMemcpyAsync(curvature, c->fe_curv.p, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-  if (picked) RG_CUDA(c, cudaMemcpyAsync(picked, c->fe_picked.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  if (label) RG_CUDA(c, cudaMemcpyAsync(label, c->fe_label.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-  if (corner && h[1] > 0) RG_CUDA(c, cudaMemcpyAsync(corner, c->fe_corner_out.p, (size_t)h[1] * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-  if (surface && h[2] > 0) RG_CUDA(c, cudaMemcpyAsync(surface, c->fe_surf_out.p, (size_t)h[2] * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));
-  return RG_OK;
-}
-
 }  // extern "C"
-
-__global__ void concat_clouds_kernel(const float4* __restrict__ a, int na, const float4* __restrict__ b, int nb, int n_pad, float4* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pad) return;
-  float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
-  if (i < na) p = a[i]; else if (i < na + nb) p = b[i - na];
-  p.w = 1.f;
-  out[i] = p;
-}
-
-extern "C" int rg_front_end_frame(rg_ctx* c, const void* raw, size_t n_points, const rg_projection_params* pp, const rg_feature_params* fp, int which,
-                                  int32_t* n_corner, int32_t* n_surface) {
-  CHECK_CTX(c);
-  if (use_device(c)) return RG_ERR_CUDA;
-  if (!pp || !fp || (!raw && n_points)) return set_err(c, RG_ERR_INVALID, "rg_front_end_frame: null argument");
-  if (pp->n_scan != fp->n_scan || pp->horizon_scan != fp->horizon_scan || pp->n_scan < 1 || pp->horizon_scan < 1 || pp->downsample_rate < 1 ||
-      pp->point_stride_bytes < 12 || pp->point_stride_bytes % 4 || pp->ring_offset_bytes < 0 || pp->ring_offset_bytes + 2 > pp->point_stride_bytes ||
-      !(fp->surf_leaf_size > 0.f))
-    return set_err(c, RG_ERR_INVALID, "rg_front_end_frame: bad parameters");
-  if (pp->horizon_scan > FE_RING_CAP) return set_err(c, RG_ERR_UNSUPPORTED, "rg_front_end_frame: horizon_scan above the per-ring capacity (2048)");
-  if (int rc = fe_alloc(c, pp->n_scan, pp->horizon_scan)) return rc;
-  const int cells = pp->n_scan * pp->horizon_scan;
-  RG_CUDA(c, c->fe_raw.ensure(c->device, std::max<size_t>(n_points * pp->point_stride_bytes, 16)));
-  if (n_points) RG_CUDA(c, cudaMemcpyAsync(c->fe_raw.p, raw, n_points * pp->point_stride_bytes, cudaMemcpyHostToDevice, c->stream));
-  RG_CUDA(c, cudaMemsetAsync(c->fe_counts.p, 0, 8 * sizeof(int), c->stream));
-  ProjLaunch P;
-  P.raw = c->fe_raw.p; P.n_points = (int)n_points; P.stride = pp->point_stride_bytes; P.ring_offset = pp->ring_offset_bytes;
-  P.n_scan = pp->n_scan; P.horizon = pp->horizon_scan; P.downsample = pp->downsample_rate; P.min_range = pp->lidar_min_range; P.max_range = pp->lidar_max_range;
-  P.owner = c->fe_owner.p; P.range_image = c->fe_range_image.p; P.full = c->fe_full.p; P.row_count = c->fe_row_count.p;
-  P.extracted = c->fe_extracted.p; P.col_ind = c->fe_col.p; P.point_range = c->fe_prange.p; P.start_ring = c->fe_start.p; P.end_ring = c->fe_end.p;
-  P.n_extracted = c->fe_counts.p;
-  RG_CUDA(c, launch_projection(P, c->stream));
-  FeatLaunch F;
-  F.extracted = c->fe_extracted.p; F.col_ind = c->fe_col.p; F.point_range = c->fe_prange.p; F.start_ring = c->fe_start.p; F.end_ring = c->fe_end.p;
-  F.n_dev = c->fe_counts.p; F.n = cells; F.n_scan = fp->n_scan; F.horizon = fp->horizon_scan;
-  F.edge_thr = fp->edge_threshold; F.surf_thr = fp->surf_threshold; F.leaf = fp->surf_leaf_size;
-  F.curvature = c->fe_curv.p; F.picked = c->fe_picked.p; F.label = c->fe_label.p;
-  F.corner_ring = c->fe_corner_ring.p; F.corner_cnt = c->fe_corner_cnt.p; F.surf_ring = c->fe_surf_ring.p; F.surf_cnt = c->fe_surf_cnt.p;
-  F.corner_out = c->fe_corner_out.p; F.n_corner = c->fe_counts.p + 1; F.surf_out = c->fe_surf_out.p; F.n_surf = c->fe_counts.p + 2;
-  F.error_flag = c->fe_counts.p + 3;
-  RG_CUDA(c, launch_features(F, c->stream));
-  g_launches += 10;
-  int h[4] = {0, 0, 0, 0};
-  RG_CUDA(c, cudaMemcpyAsync(h, c->fe_counts.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (h[3] != 0) return set_err(c, RG_ERR_UNSUPPORTED, "rg_front_end_frame: sector/ring capacity exceeded");
-  if (n_corner) *n_corner = h[1];
-  if (n_surface) *n_surface = h[2];
-  c->fe_frame_ok = true; c->fe_n_scan = pp->n_scan; c->fe_n[0] = h[0]; c->fe_n[1] = h[1]; c->fe_n[2] = h[2];
-  Cloud& cl = which == RG_SOURCE ? c->src : c->tgt;
-  const int n = h[1] + h[2];
-  const int n_pad = (n + TILE_PTS - 1) / TILE_PTS * TILE_PTS;
-  RG_CUDA(c, cl.pts.ensure(c->device, std::max(n_pad, TILE_PTS)));
-  RG_CUDA(c, cl.cov6.ensure(c->device, (size_t)std::max(n_pad, TILE_PTS) * COV_PLANES));
-  cl.n = n; cl.n_pad = n_pad; cl.has_cov = false; cl.host_identity = nullptr;
-  if (n > 0) {
-    g_launches++;
-    concat_clouds_kernel<<<(n_pad + 255) / 256, 256, 0, c->stream>>>(c->fe_corner_out.p, h[1], c->fe_surf_out.p, h[2], n_pad, cl.pts.p);
-    RG_CUDA(c, cudaGetLastError());
-  }
-  if (which == RG_TARGET) c->voxel_ok = false;
-  c->st_ok = false; c->have_corr = false;
-  if (which == RG_SOURCE) c->shard_lo = c->shard_hi = 0;
-  return RG_OK;
-}
-
-// ---- rolo/CloudInfoStamp wire image at the ROS edge (cloud_info.hpp) ------------------------------------------------
-
-// float4 (x, y, z, intensity) -> 32-byte pcl::PointXYZI record (x y z 1 | intensity 0 0 0)
-__global__ void pack_xyzi_kernel(const float4* __restrict__ in, int n, float4* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 p = in[i];
-  out[2 * i] = make_float4(p.x, p.y, p.z, 1.f);
-  out[2 * i + 1] = make_float4(p.w, 0.f, 0.f, 0.f);
-}
-
-struct WireCloud { const unsigned char* data; int n, step, ox, oy, oz; };
-
-// corner + surface point records of a serialised message -> the context's float4 cloud (featureLast = corner + surf)
-__global__ void unpack_features_kernel(WireCloud a, WireCloud b, int n_pad, float4* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pad) return;
-  float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
-  const WireCloud* w = nullptr; int j = 0;
-  if (i < a.n) { w = &a; j = i; } else if (i < a.n + b.n) { w = &b; j = i - a.n; }
-  if (w) {
-    const unsigned char* r = w->data + (size_t)j * w->step;
-    p.x = *reinterpret_cast<const float*>(r + w->ox); p.y = *reinterpret_cast<const float*>(r + w->oy); p.z = *reinterpret_cast<const float*>(r + w->oz);
-  }
-  out[i] = p;
-}
-
-extern "C" int rg_cloud_info_serialize(rg_ctx* c, int stage, const rg_msg_header* hdr, const rg_cloud_info_scalars* sc, uint8_t* out, size_t capacity,
-                                       size_t* written) {
-  CHECK_CTX(c);
-  if (use_device(c)) return RG_ERR_CUDA;
-  if (!hdr || !written || (stage != 0 && stage != 1)) return set_err(c, RG_ERR_INVALID, "rg_cloud_info_serialize: bad arguments");
-  if (!c->fe_frame_ok) return set_err(c, RG_ERR_INVALID, "rg_cloud_info_serialize: no front-end frame resident (call rg_front_end_frame first)");
-  static const float no_cov[1] = {0.f};
-  wire::Scalars s{};
-  if (sc) {
-    s.startOrientation = sc->start_orientation; s.endOrientation = sc->end_orientation; s.orientationDiff = sc->orientation_diff;
-    for (int i = 0; i < 6; i++) s.initialGuess[i] = sc->initial_guess[i];
-    s.covariance = sc->n_covariance ? sc->covariance : no_cov; s.n_covariance = sc->n_covariance; s.odomAvailable = sc->odom_available;
-    if (sc->n_covariance && !sc->covariance) return set_err(c, RG_ERR_INVALID, "rg_cloud_info_serialize: null covariance");
-  } else { s.covariance = no_cov; }
-  const char* frame = hdr->frame_id ? hdr->frame_id : "";
-  const wire::Header h{hdr->seq, hdr->stamp_sec, hdr->stamp_nsec, frame, std::strlen(frame)};
-  wire::Sections sec;
-  wire::Writer w(out, capacity);
-  const size_t total = wire::write_cloud_info(w, stage, h, s, (uint32_t)c->fe_n_scan, (uint32_t)c->fe_n[0], (uint32_t)c->fe_n[1], (uint32_t)c->fe_n[2], sec);
-  *written = total;
-  if (!out) return RG_OK;
-  if (w.overflow) return set_err(c, RG_ERR_INVALID, "rg_cloud_info_serialize: output buffer too small");
-  const int n0 = c->fe_n[0], n1 = stage == 1 ? c->fe_n[1] : 0, n2 = stage == 1 ? c->fe_n[2] : 0;
-  const size_t recs = (size_t)n0 + n1 + n2;
-  RG_CUDA(c, c->fe_wire.ensure(c->device, std::max<size_t>(recs * wire::POINT_STEP, 32)));
-  float4* stage_buf = reinterpret_cast<float4*>(c->fe_wire.p);
-  const struct { const float4* src; int n; size_t off; } part[3] = {{c->fe_extracted.p, n0, sec.projected}, {c->fe_corner_out.p, n1, sec.corner}, {c->fe_surf_out.p, n2, sec.surface}};
-  size_t rec0 = 0;
-  for (int k = 0; k < 3; k++) {
-    if (part[k].n <= 0) continue;
-    g_launches++;
-    pack_xyzi_kernel<<<(part[k].n + 255) / 256, 256, 0, c->stream>>>(part[k].src, part[k].n, stage_buf + 2 * rec0);
-    RG_CUDA(c, cudaGetLastError());
-    RG_CUDA(c, cudaMemcpyAsync(out + part[k].off, stage_buf + 2 * rec0, (size_t)part[k].n * wire::POINT_STEP, cudaMemcpyDeviceToHost, c->stream));
-    rec0 += part[k].n;
-  }
-  if (stage == 0) {
-    RG_CUDA(c, cudaMemcpyAsync(out + sec.start_ring, c->fe_start.p, 4ull * c->fe_n_scan, cudaMemcpyDeviceToHost, c->stream));
-    RG_CUDA(c, cudaMemcpyAsync(out + sec.end_ring, c->fe_end.p, 4ull * c->fe_n_scan, cudaMemcpyDeviceToHost, c->stream));
-    if (n0 > 0) {
-      RG_CUDA(c, cudaMemcpyAsync(out + sec.col_ind, c->fe_col.p, 4ull * n0, cudaMemcpyDeviceToHost, c->stream));
-      RG_CUDA(c, cudaMemcpyAsync(out + sec.point_range, c->fe_prange.p, 4ull * n0, cudaMemcpyDeviceToHost, c->stream));
-    }
-  }
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));
-  return RG_OK;
-}
-
-extern "C" int rg_set_input_from_cloud_info(rg_ctx* c, int which, const uint8_t* msg, size_t len, int32_t* n_corner, int32_t* n_surface) {
-  CHECK_CTX(c);
-  if (use_device(c)) return RG_ERR_CUDA;
-  if (!msg || (which != RG_SOURCE && which != RG_TARGET)) return set_err(c, RG_ERR_INVALID, "rg_set_input_from_cloud_info: bad arguments");
-  wire::Parsed P;
-  if (!wire::parse_cloud_info(msg, len, P)) return set_err(c, RG_ERR_INVALID, "rg_set_input_from_cloud_info: malformed CloudInfoStamp message");
-  const wire::CloudView* cv[2] = {&P.corner, &P.surface};
-  for (int k = 0; k < 2; k++) {
-    const wire::CloudView& v = *cv[k];
-    if (v.n_points == 0) continue;
-    if (v.off_x < 0 || v.off_y < 0 || v.off_z < 0 || (v.off_x | v.off_y | v.off_z | (int)v.point_step) % 4 != 0 ||
-        (uint32_t)std::max(v.off_x, std::max(v.off_y, v.off_z)) + 4 > v.point_step)
-      return set_err(c, RG_ERR_UNSUPPORTED, "rg_set_input_from_cloud_info: feature clouds need 4-byte aligned float32 x/y/z fields");
-  }
-  const size_t bytes_a = (size_t)P.corner.n_points * P.corner.point_step, bytes_b = (size_t)P.surface.n_points * P.surface.point_step;
-  const size_t off_b = (bytes_a + 15) / 16 * 16;
-  RG_CUDA(c, c->fe_wire.ensure(c->device, std::max<size_t>(off_b + bytes_b, 32)));
-  if (bytes_a) RG_CUDA(c, cudaMemcpyAsync(c->fe_wire.p, msg + P.corner.data, bytes_a, cudaMemcpyHostToDevice, c->stream));
-  if (bytes_b) RG_CUDA(c, cudaMemcpyAsync(c->fe_wire.p + off_b, msg + P.surface.data, bytes_b, cudaMemcpyHostToDevice, c->stream));
-  Cloud& cl = which == RG_SOURCE ? c->src : c->tgt;
-  const int n = (int)(P.corner.n_points + P.surface.n_points);
-  const int n_pad = (n + TILE_PTS - 1) / TILE_PTS * TILE_PTS;
-  RG_CUDA(c, cl.pts.ensure(c->device, std::max(n_pad, TILE_PTS)));
-  RG_CUDA(c, cl.cov6.ensure(c->device, (size_t)std::max(n_pad, TILE_PTS) * COV_PLANES));
-  cl.n = n; cl.n_pad = n_pad; cl.has_cov = false; cl.host_identity = nullptr;
-  if (n > 0) {
-    const WireCloud a{c->fe_wire.p, (int)P.corner.n_points, (int)P.corner.point_step, P.corner.off_x, P.corner.off_y, P.corner.off_z};
-    const WireCloud b{c->fe_wire.p + off_b, (int)P.surface.n_points, (int)P.surface.point_step, P.surface.off_x, P.surface.off_y, P.surface.off_z};
-    g_launches++;
-    unpack_features_kernel<<<(n_pad + 255) / 256, 256, 0, c->stream>>>(a, b, n_pad, cl.pts.p);
-    RG_CUDA(c, cudaGetLastError());
-  }
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));      // msg may be pageable and reused by the caller
-  if (n_corner) *n_corner = (int32_t)P.corner.n_points;
-  if (n_surface) *n_surface = (int32_t)P.surface.n_points;
-  if (which == RG_TARGET) c->voxel_ok = false;
-  c->st_ok = false; c->have_corr = false;
-  if (which == RG_SOURCE) c->shard_lo = c->shard_hi = 0;
-  return RG_OK;
-}
-
-// ---- backMapping scan-to-map optimisation (backMapping.cpp:681-1054) ------------------------------
-
-extern "C" int rg_s2m_set_map(rg_ctx* c, const float* corner, size_t n_corner, const float* surf, size_t n_surf, size_t stride_bytes) {
-  CHECK_CTX(c);
-  if (use_device(c)) return RG_ERR_CUDA;
-  c->s2m_map_ok = false; c->s2m_lin_ok = false;
-  const float* src[2] = {corner, surf}; const size_t cnt[2] = {n_corner, n_surf};
-  for (int m = 0; m < 2; m++) {
-    if (int rc = upload_cloud(c, c->s2m_cloud[m], src[m], cnt[m], stride_bytes)) return rc;
-    const int n = (int)cnt[m];
-    if (n == 0) continue;
-    // kdtree*FromMap->setInputCloud (backMapping.cpp:689-690): here the Morton index of covariance.cu
-    RG_CUDA(c, c->codes_in.ensure(c->device, n)); RG_CUDA(c, c->idx_in.ensure(c->device, n)); RG_CUDA(c, c->idx_out.ensure(c->device, n));
-    RG_CUDA(c, c->s2m_codes[m].ensure(c->device, n)); RG_CUDA(c, c->s2m_sorted[m].ensure(c->device, n));
-    RG_CUDA(c, c->s2m_bbox[m].ensure(c->device, 8)); RG_CUDA(c, c->s2m_bucket[m].ensure(c->device, cov_bucket_table_entries()));
-    const size_t tb = cov_cub_temp_bytes(n);
-    RG_CUDA(c, c->cub_temp.ensure(c->device, tb));
-    CovScratch sc;
-    sc.codes_in = c->codes_in.p; sc.codes_out = c->s2m_codes[m].p; sc.idx_in = c->idx_in.p; sc.idx_out = c->idx_out.p; sc.sorted = c->s2m_sorted[m].p;
-    sc.cub_temp = c->cub_temp.p; sc.cub_temp_bytes = tb; sc.bbox = c->s2m_bbox[m].p; sc.bucket_start = c->s2m_bucket[m].p;
-    RG_CUDA(c, launch_sort_cloud(c->s2m_cloud[m].pts.p, n, sc, true, c->stream));
-    g_launches += 5;
-  }
-  c->s2m_map_ok = true;
-  return RG_OK;
-}
-
-extern "C" int rg_s2m_set_scan(rg_ctx* c, const float* corner, size_t n_corner, const float* surf, size_t n_surf, size_t stride_bytes) {
-  CHECK_CTX(c);
-  if (use_device(c)) return RG_ERR_CUDA;
-  c->s2m_scan_ok = false; c->s2m_lin_ok = false;
-  // the intensity column is not used by the optimisation: xyz only
-  if (int rc = upload_cloud(c, c->s2m_cloud[2], corner, n_corner, stride_bytes)) return rc;
-  if (int rc = upload_cloud(c, c->s2m_cloud[3], surf, n_surf, stride_bytes)) return rc;
-  for (int m = 0; m < 2; m++) {
-    RG_CUDA(c, c->s2m_coeff[m].ensure(c->device, std::max(c->s2m_cloud[2 + m].n, 1)));
-    RG_CUDA(c, c->s2m_flag[m].ensure(c->device, std::max(c->s2m_cloud[2 + m].n, 1)));
-  }
-  c->s2m_scan_ok = true;
-  return RG_OK;
-}
-
-// one kernel launch = cornerOptimization + surfOptimization + combineOptimizationCoeffs + the AtA/AtB assembly at pose tf
-static int s2m_evaluate(rg_ctx* c, const float tf[6], float AtA[36], float AtB[6], int* n_sel) {
-  if (!c->s2m_map_ok || !c->s2m_scan_ok) return set_err(c, RG_ERR_INVALID, "scan-to-map: call rg_s2m_set_map and rg_s2m_set_scan first");
-  const size_t s2m_total = (size_t)c->s2m_cloud[2].n + c->s2m_cloud[3].n;
-  RG_CUDA(c, c->s2m_partial.ensure(c->device, ((s2m_total + S2M_FIT_THREADS_PER_BLOCK - 1) / S2M_FIT_THREADS_PER_BLOCK + 1) * S2M_RES));
-  RG_CUDA(c, c->s2m_nn.ensure(c->device, std::max<size_t>(s2m_total * 5, 8)));
-  RG_CUDA(c, c->s2m_result.ensure(c->device, S2M_RES));
-  if (!c->s2m_counter.p) {
-    RG_CUDA(c, c->s2m_counter.ensure(c->device, 1));
-    RG_CUDA(c, cudaMemsetAsync(c->s2m_counter.p, 0, sizeof(unsigned), c->stream));
-  }
-  S2MLaunch L;
-  for (int m = 0; m < 2; m++) {
-    L.map[m].pts = c->s2m_cloud[m].pts.p; L.map[m].sorted = c->s2m_sorted[m].p; L.map[m].codes = c->s2m_codes[m].p;
-    L.map[m].bucket_start = c->s2m_bucket[m].p; L.map[m].bbox = c->s2m_bbox[m].p; L.map[m].n = c->s2m_cloud[m].n;
-    L.scan[m] = c->s2m_cloud[2 + m].pts.p; L.n_scan[m] = c->s2m_cloud[2 + m].n;
-    L.coeff[m] = c->s2m_coeff[m].p; L.flag[m] = c->s2m_flag[m].p;
-  }
-  s2m::get_transformation(tf, L.t);
-  // LMOptimization's six sines / cosines (backMapping.cpp:949-954), evaluated on the host like the reference does
-  L.sc[0] = sinf(tf[1]); L.sc[1] = cosf(tf[1]); L.sc[2] = sinf(tf[2]); L.sc[3] = cosf(tf[2]); L.sc[4] = sinf(tf[0]); L.sc[5] = cosf(tf[0]);
-  L.nn = c->s2m_nn.p; L.partial = c->s2m_partial.p; L.counter = c->s2m_counter.p; L.result = c->s2m_result.p;
-  RG_CUDA(c, launch_scan2map(L, c->stream));
-  g_launches += 2;
-  double r[S2M_RES];
-  RG_CUDA(c, cudaMemcpyAsync(r, c->s2m_result.p, sizeof(r), cudaMemcpyDeviceToHost, c->stream));
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));
-  int t = 0;
-  for (int a = 0; a < 6; a++) for (int b = a; b < 6; b++, t++) AtA[a * 6 + b] = AtA[b * 6 + a] = (float)r[t];   // cv::gemm: double sums, float result
-  for (int a = 0; a < 6; a++) AtB[a] = (float)r[21 + a];
-  *n_sel = (int)(r[27] + 0.5);
-  c->s2m_lin_ok = true;
-  return RG_OK;
-}
-
-extern "C" int rg_s2m_linearize(rg_ctx* c, const float tf[6], float AtA[36], float AtB[6], int32_t* n_selected) {
-  CHECK_CTX(c);
-  if (use_device(c)) return RG_ERR_CUDA;
-  if (!tf || !AtA || !AtB || !n_selected) return set_err(c, RG_ERR_INVALID, "rg_s2m_linearize: null argument");
-  int n = 0;
-  if (int rc = s2m_evaluate(c, tf, AtA, AtB, &n)) return rc;
-  *n_selected = n;
-  return RG_OK;
-}
-
-extern "C" int rg_s2m_get_coefficients(rg_ctx* c, float* coeff_corner, uint8_t* flag_corner, float* coeff_surf, uint8_t* flag_surf) {
-  CHECK_CTX(c);
-  if (use_device(c)) return RG_ERR_CUDA;
-  if (!c->s2m_lin_ok) return set_err(c, RG_ERR_INVALID, "rg_s2m_get_coefficients: no evaluation yet");
-  float* cf[2] = {coeff_corner, coeff_surf}; uint8_t* fl[2] = {flag_corner, flag_surf};
-  for (int m = 0; m < 2; m++) {
-    const int n = c->s2m_cloud[2 + m].n;
-    if (n == 0) continue;
-    if (cf[m]) RG_CUDA(c, cudaMemcpyAsync(cf[m], c->s2m_coeff[m].p, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    if (fl[m]) RG_CUDA(c, cudaMemcpyAsync(fl[m], c->s2m_flag[m].p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-  }
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));
-  return RG_OK;
-}
-
-// scan2MapOptimization (backMapping.cpp:681-710) + LMOptimization (:937-1054); transformUpdate()'s IMU blend is not part of it
-extern "C" int rg_s2m_optimize(rg_ctx* c, float tf[6], int max_iterations, int edge_feature_min, int surf_feature_min, rg_s2m_result* out) {
-  CHECK_CTX(c);
-  if (use_device(c)) return RG_ERR_CUDA;
-  if (!tf || !out || max_iterations < 0) return set_err(c, RG_ERR_INVALID, "rg_s2m_optimize: bad arguments");
-  if (!c->s2m_map_ok || !c->s2m_scan_ok) return set_err(c, RG_ERR_INVALID, "scan-to-map: call rg_s2m_set_map and rg_s2m_set_scan first");
-  out->iterations = 0; out->converged = 0; out->degenerate = 0; out->enough_features = 0;
-  if (!(c->s2m_cloud[2].n > edge_feature_min && c->s2m_cloud[3].n > surf_feature_min)) return RG_OK;   // "Not enough features!" (:687,705-707)
-  out->enough_features = 1;
-  bool degenerate = false;
-  float matP[36];
-  for (int iter = 0; iter < max_iterations; iter++) {
-    float AtA[36], AtB[6], X[6];
-    int sel = 0;
-    if (int rc = s2m_evaluate(c, tf, AtA, AtB, &sel)) return rc;
-    out->iterations++;
-    if (sel < 50) continue;                                                       // :956-958
-    { float A[36], b[6]; std::memcpy(A, AtA, sizeof(A)); std::memcpy(b, AtB, sizeof(b)); s2m::qr_solve<6, 6, false>(A, b, X); }   // cv::solve(DECOMP_QR)
-    if (iter == 0) {                                                              // degeneracy analysis, first iteration only (:1008-1029)
-      float A[36], E[6], V[36], V2[36], Vi[36];
-      std::memcpy(A, AtA, sizeof(A));
-      s2m::jacobi_eigen<6>(A, E, V);
-      std::memcpy(V2, V, sizeof(V2));
-      degenerate = false;
-      for (int i = 5; i >= 0; i--) {
-        if (E[i] < 100.f) { for (int j = 0; j < 6; j++) V2[i * 6 + j] = 0.f; degenerate = true; } else break;
-      }
-      if (!s2m::invert_lu<6>(V, Vi)) std::memset(Vi, 0, sizeof(Vi));
-      for (int a = 0; a < 6; a++)
-        for (int b = 0; b < 6; b++) { double acc = 0.0; for (int k = 0; k < 6; k++) acc += (double)Vi[a * 6 + k] * (double)V2[k * 6 + b]; matP[a * 6 + b] = (float)acc; }
-    }
-    if (degenerate) {
-      float X2[6]; std::memcpy(X2, X, sizeof(X2));
-      for (int a = 0; a < 6; a++) { double acc = 0.0; for (int k = 0; k < 6; k++) acc += (double)matP[a * 6 + k] * (double)X2[k]; X[a] = (float)acc; }
-    }
-    for (int a = 0; a < 6; a++) tf[a] += X[a];
-    const float r0 = X[0] * 57.29578f, r1 = X[1] * 57.29578f, r2 = X[2] * 57.29578f, c0 = X[3] * 100, c1 = X[4] * 100, c2 = X[5] * 100;
-    const float deltaR = (float)std::sqrt((double)r0 * r0 + (double)r1 * r1 + (double)r2 * r2);
-    const float deltaT = (float)std::sqrt((double)c0 * c0 + (double)c1 * c1 + (double)c2 * c2);
-    if ((double)deltaR < 0.05 && (double)deltaT < 0.05) { out->converged = 1; break; }
-  }
-  out->degenerate = degenerate ? 1 : 0;
-  return RG_OK;
-}
-
-// ---- Scan Context place recognition (src/scancontext/Scancontext.cpp) ------------------------------
-
-extern "C" int rg_sc_make_and_save(rg_ctx* c, const float* pts, size_t n, size_t stride_bytes, double lidar_height) {
-  CHECK_CTX(c);
-  if (use_device(c)) return RG_ERR_CUDA;
-  if (int rc = upload_cloud(c, c->sc_cloud, pts, n, stride_bytes)) return rc;
-  RG_CUDA(c, c->sc_bins.ensure(c->device, SC_BINS));
-  RG_CUDA(c, c->sc_out.ensure(c->device, SC_BINS + SC_NUM_RING + SC_NUM_SECTOR));
-  SCLaunch L;
-  L.pts = c->sc_cloud.pts.p; L.n = (int)n; L.lidar_height = lidar_height; L.max_radius = 80.0;   // PC_MAX_RADIUS (Scancontext.h:84)
-  L.bins = c->sc_bins.p; L.desc = c->sc_out.p; L.ring_key = c->sc_out.p + SC_BINS; L.sector_key = c->sc_out.p + SC_BINS + SC_NUM_RING;
-  RG_CUDA(c, launch_scancontext(L, c->stream));
-  g_launches += 3;
-  double h[SC_BINS + SC_NUM_RING + SC_NUM_SECTOR];
-  RG_CUDA(c, cudaMemcpyAsync(h, c->sc_out.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));
-  sc::Entry e;
-  std::memcpy(e.desc, h, sizeof(e.desc)); std::memcpy(e.ring_key, h + SC_BINS, sizeof(e.ring_key)); std::memcpy(e.sector_key, h + SC_BINS + SC_NUM_RING, sizeof(e.sector_key));
-  for (int k = 0; k < SC_NUM_RING; k++) e.ring_key_f[k] = (float)e.ring_key[k];      // eig2stdvec (Scancontext.cpp:62-66)
-  c->sc_mgr.entries.push_back(e);
-  return RG_OK;
-}
-
-extern "C" int rg_sc_size(rg_ctx* c) { return c ? (int)c->sc_mgr.entries.size() : 0; }
-
-extern "C" int rg_sc_clear(rg_ctx* c) {
-  CHECK_CTX(c);
-  c->sc_mgr = sc::Manager();
-  return RG_OK;
-}
-
-static const sc::Entry* sc_entry(rg_ctx* c, int index) {
-  const int n = (int)c->sc_mgr.entries.size();
-  if (index < 0) index += n;
-  return (index >= 0 && index < n) ? &c->sc_mgr.entries[index] : nullptr;
-}
-
-extern "C" int rg_sc_get(rg_ctx* c, int index, double* desc, double* ring_key, double* sector_key) {
-  CHECK_CTX(c);
-  const sc::Entry* e = sc_entry(c, index);
-  if (!e) return set_err(c, RG_ERR_INVALID, "rg_sc_get: no such descriptor");
-  if (desc) std::memcpy(desc, e->desc, sizeof(e->desc));
-  if (ring_key) std::memcpy(ring_key, e->ring_key, sizeof(e->ring_key));
-  if (sector_key) std::memcpy(sector_key, e->sector_key, sizeof(e->sector_key));
-  return RG_OK;
-}
-
-extern "C" int rg_sc_distance(rg_ctx* c, int i, int j, double* dist, int32_t* shift) {
-  CHECK_CTX(c);
-  const sc::Entry *a = sc_entry(c, i), *b = sc_entry(c, j);
-  if (!a || !b || !dist || !shift) return set_err(c, RG_ERR_INVALID, "rg_sc_distance: bad arguments");
-  const std::pair<double, int> r = sc::distance(*a, *b);
-  *dist = r.first; *shift = r.second;
-  return RG_OK;
-}
-
-extern "C" int rg_sc_detect(rg_ctx* c, int32_t* loop_id, float* yaw_diff_rad) {
-  CHECK_CTX(c);
-  if (!loop_id || !yaw_diff_rad) return set_err(c, RG_ERR_INVALID, "rg_sc_detect: null argument");
-  if (c->sc_mgr.entries.empty()) return set_err(c, RG_ERR_INVALID, "rg_sc_detect: no descriptor saved yet");
-  const std::pair<int, float> r = c->sc_mgr.detect();
-  *loop_id = r.first; *yaw_diff_rad = r.second;
-  return RG_OK;
-}
-
-// ---- pcl::Registration::getFitnessScore / loop-closure verification (backMapping.cpp:2351,2428) -------
-
-// nearest target point of every source point moved by T (row-major 4x4 float)
-static int nearest_target(rg_ctx* c, const float T[16]) {
-  if (c->src.n == 0 || c->tgt.n == 0) return set_err(c, RG_ERR_INVALID, "fitness score: source and target clouds must be set");
-  const int n = c->tgt.n, nq = c->src.n;
-  RG_CUDA(c, c->codes_in.ensure(c->device, n)); RG_CUDA(c, c->idx_in.ensure(c->device, n)); RG_CUDA(c, c->idx_out.ensure(c->device, n));
-  RG_CUDA(c, c->fit_codes.ensure(c->device, n)); RG_CUDA(c, c->fit_sorted.ensure(c->device, n));
-  RG_CUDA(c, c->fit_bbox.ensure(c->device, 8)); RG_CUDA(c, c->fit_bucket.ensure(c->device, cov_bucket_table_entries()));
-  const size_t tb = cov_cub_temp_bytes(n);
-  RG_CUDA(c, c->cub_temp.ensure(c->device, tb));
-  RG_CUDA(c, c->fit_idx.ensure(c->device, nq)); RG_CUDA(c, c->fit_d2.ensure(c->device, nq)); RG_CUDA(c, c->fit_T.ensure(c->device, 12));
-  CovScratch sc;
-  sc.codes_in = c->codes_in.p; sc.codes_out = c->fit_codes.p; sc.idx_in = c->idx_in.p; sc.idx_out = c->idx_out.p; sc.sorted = c->fit_sorted.p;
-  sc.cub_temp = c->cub_temp.p; sc.cub_temp_bytes = tb; sc.bbox = c->fit_bbox.p; sc.bucket_start = c->fit_bucket.p;
-  RG_CUDA(c, launch_sort_cloud(c->tgt.pts.p, n, sc, true, c->stream));          // tree_->setInputCloud(target_) of pcl::Registration
-  RG_CUDA(c, cudaMemcpyAsync(c->fit_T.p, T, 12 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  RG_CUDA(c, launch_nearest(c->src.pts.p, nq, c->fit_T.p, sc, n, c->fit_idx.p, c->fit_d2.p, c->stream));
-  g_launches += 6;
-  return RG_OK;
-}
-
-extern "C" int rg_nearest_target(rg_ctx* c, const float T[16], int32_t* idx, float* sq_dist) {
-  CHECK_CTX(c);
-  if (use_device(c)) return RG_ERR_CUDA;
-  if (!T) return set_err(c, RG_ERR_INVALID, "rg_nearest_target: null transform");
-  if (int rc = nearest_target(c, T)) return rc;
-  if (idx) RG_CUDA(c, cudaMemcpyAsync(idx, c->fit_idx.p, sizeof(int) * (size_t)c->src.n, cudaMemcpyDeviceToHost, c->stream));
-  if (sq_dist) RG_CUDA(c, cudaMemcpyAsync(sq_dist, c->fit_d2.p, sizeof(float) * (size_t)c->src.n, cudaMemcpyDeviceToHost, c->stream));
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));
-  return RG_OK;
-}
-
-extern "C" int rg_get_fitness_score(rg_ctx* c, const float T[16], double max_range, double* score) {
-  CHECK_CTX(c);
-  if (use_device(c)) return RG_ERR_CUDA;
-  if (!T || !score) return set_err(c, RG_ERR_INVALID, "rg_get_fitness_score: null argument");
-  if (int rc = nearest_target(c, T)) return rc;
-  std::vector<float> d2((size_t)c->src.n);
-  RG_CUDA(c, cudaMemcpyAsync(d2.data(), c->fit_d2.p, sizeof(float) * d2.size(), cudaMemcpyDeviceToHost, c->stream));
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));
-  // the reference's accumulation: doubles, in point order, squared distance compared with max_range as is
-  double fitness = 0.0; int nr = 0;
-  for (float d : d2) if ((double)d <= max_range) { fitness += (double)d; nr++; }
-  *score = nr > 0 ? fitness / nr : 1.7976931348623157e308;
-  return RG_OK;
-}
