@@ -191,8 +191,8 @@ int rg_shard_export(rg_ctx*, void* ipc_handle_64_bytes);
 int rg_shard_connect(rg_ctx*, int rank, int world, const void* ipc_handles /* world x 64 bytes */);
 
 /* ---- upstream range-image passes ------------------------------------------------------------------------ */
-/* ImageProjection::projectPointCloud + cloudExtraction (imageProjection.cpp:399-505), deskew disabled
- * (config/params.yaml:25). Raw points: x,y,z float at byte offsets 0,4,8; ring uint16 at ring_offset.
+/* ImageProjection::projectPointCloud + cloudExtraction (imageProjection.cpp:399-505); deskew off unless rg_set_deskew was called
+ * (config/params.yaml:25 ships it disabled). Raw points: x,y,z float at byte offsets 0,4,8; ring uint16 at ring_offset.
  * Outputs (host): range image float[n_scan*horizon] (FLT_MAX = empty), extracted cloud float4 xyz+intensity
  * (intensity = ring*z, imageProjection.cpp:410), point_col_ind int32, point_range float, start/end ring index. */
 typedef struct rg_projection_params {
@@ -200,6 +200,16 @@ typedef struct rg_projection_params {
   float lidar_min_range, lidar_max_range;
   int point_stride_bytes, ring_offset_bytes;
 } rg_projection_params;
+/* deskewPoint (imageProjection.cpp:368-396): with deskewEnabled && odomAvailable every projected point is rotated back by the
+ * odometry increment (roll, pitch, yaw) scaled to its time within the sweep; translation is not compensated in the reference.
+ * NULL (the default, config/params.yaml:25) disables it. Applies to rg_image_projection and rg_front_end_frame. */
+typedef struct rg_deskew_params {
+  int time_offset_bytes;                                     /* float relative time of the point (VelodynePointXYZIRT::time: 24) */
+  float odom_incre_roll, odom_incre_pitch, odom_incre_yaw;   /* odomIncreRoll/Pitch/Yaw (:299,351) */
+  float scan_period;                                         /* :79 */
+  double odom_time_diff;                                     /* :298,350 */
+} rg_deskew_params;
+int rg_set_deskew(rg_ctx*, const rg_deskew_params* p);
 int rg_image_projection(rg_ctx*, const void* host_raw_points, size_t n_points, const rg_projection_params* p,
                         float* range_image, float* extracted_xyzi, int32_t* point_col_ind, float* point_range,
                         int32_t* start_ring_index, int32_t* end_ring_index, int32_t* n_extracted);

@@ -243,7 +243,8 @@ def ldlt_solve(A, b):
 
 
 # ---- upstream range-image passes (oracle/frontend_oracle.cpp) ---------------------------------------
-def image_projection(raw: np.ndarray, n_scan, horizon, downsample_rate=1, min_range=2.0, max_range=1000.0, ring_offset=20):
+def image_projection(raw: np.ndarray, n_scan, horizon, downsample_rate=1, min_range=2.0, max_range=1000.0, ring_offset=20, deskew=None):
+    """deskew = None (deskewEnabled false / no odometry) or dict(time_offset, incre_rpy(3), scan_period, odom_time_diff)."""
     L = lib()
     raw = np.ascontiguousarray(raw)
     cells = n_scan * horizon
@@ -251,8 +252,15 @@ def image_projection(raw: np.ndarray, n_scan, horizon, downsample_rate=1, min_ra
     ext = np.empty((cells, 4), dtype=np.float32); col = np.empty(cells, dtype=np.int32); rng = np.empty(cells, dtype=np.float32)
     st = np.empty(n_scan, dtype=np.int32); en = np.empty(n_scan, dtype=np.int32)
     vp = lambda a: C.c_void_p(a.ctypes.data)
-    n = L.ro_image_projection(vp(raw), C.c_size_t(raw.shape[0]), C.c_int(raw.dtype.itemsize), C.c_int(ring_offset), C.c_int(n_scan), C.c_int(horizon),
-                              C.c_int(downsample_rate), C.c_float(min_range), C.c_float(max_range), vp(rim), vp(ext), vp(col), vp(rng), vp(st), vp(en))
+    if deskew is None:
+        n = L.ro_image_projection(vp(raw), C.c_size_t(raw.shape[0]), C.c_int(raw.dtype.itemsize), C.c_int(ring_offset), C.c_int(n_scan), C.c_int(horizon),
+                                  C.c_int(downsample_rate), C.c_float(min_range), C.c_float(max_range), vp(rim), vp(ext), vp(col), vp(rng), vp(st), vp(en))
+    else:
+        inc = np.ascontiguousarray(deskew["incre_rpy"], dtype=np.float32)
+        n = L.ro_image_projection_deskew(vp(raw), C.c_size_t(raw.shape[0]), C.c_int(raw.dtype.itemsize), C.c_int(ring_offset), C.c_int(n_scan), C.c_int(horizon),
+                                         C.c_int(downsample_rate), C.c_float(min_range), C.c_float(max_range), C.c_int(1), C.c_int(deskew["time_offset"]),
+                                         vp(inc), C.c_float(deskew["scan_period"]), C.c_double(deskew["odom_time_diff"]),
+                                         vp(rim), vp(ext), vp(col), vp(rng), vp(st), vp(en))
     return {"range_image": rim, "extracted": ext[:n].copy(), "point_col_ind": col[:n].copy(), "point_range": rng[:n].copy(),
             "start_ring_index": st, "end_ring_index": en, "n": n}
 

@@ -1,6 +1,6 @@
 // frontend_oracle.cpp — CPU ORACLE (test infrastructure, NOT product code) for the two upstream
 // range-image passes of sdwyc/ROLO @ 3920bb7:
-//   src/imageProjection.cpp   projectPointCloud :399-474, cloudExtraction :477-505 (deskew disabled,
+//   src/imageProjection.cpp   projectPointCloud :399-474, cloudExtraction :477-505 (deskew disabled by default,
 //                             config/params.yaml:25; deskewPoint :368-396 returns the point unchanged then)
 //   src/featureExtraction.cpp calculateSmoothness :87-110, markOccludedPoints :112-150,
 //                             extractFeatures :153-266
@@ -26,10 +26,38 @@
 
 extern "C" {
 
+// deskewPoint (imageProjection.cpp:368-396) for deskewEnabled && odomAvailable: rotation-only correction by the odometry
+// increment scaled to the point's time; sin/cos are the correctly rounded float values (double libm rounded once)
+static void deskew_point(float& x, float& y, float& z, double relTime, const float incre_rpy[3], float scanPeriod, double odomTimeDiff) {
+  const float ratio = relTime / scanPeriod;                                       // :380
+  const float k = scanPeriod / odomTimeDiff;                                      // Eigen takes the scalar as float (:383)
+  const float roll = -((incre_rpy[0] * k) * ratio), pitch = -((incre_rpy[1] * k) * ratio), yaw = -((incre_rpy[2] * k) * ratio);
+  auto cs = [](float a) { return (float)std::cos((double)a); };
+  auto sn = [](float a) { return (float)std::sin((double)a); };
+  const float A = cs(yaw), B = sn(yaw), C = cs(pitch), D = sn(pitch), E = cs(roll), F = sn(roll), DE = D * E, DF = D * F;   // pcl::getTransformation
+  const float t00 = A * C, t01 = A * DF - B * E, t02 = B * F + A * DE, t10 = B * C, t11 = A * E + B * DF, t12 = B * DE - A * F, t20 = -D, t21 = C * F, t22 = C * E;
+  const float nx = t00 * x + t01 * y + t02 * z + 0.0f, ny = t10 * x + t11 * y + t12 * z + 0.0f, nz = t20 * x + t21 * y + t22 * z + 0.0f;   // :388-390
+  x = nx; y = ny; z = nz;
+}
+
+int ro_image_projection_deskew(const void* raw, size_t n_points, int stride_bytes, int ring_offset_bytes, int n_scan, int horizon_scan,
+                               int downsample_rate, float lidar_min_range, float lidar_max_range, int deskew, int time_offset_bytes,
+                               const float* incre_rpy, float scan_period, double odom_time_diff, float* range_image,
+                               float* extracted_xyzi, int* point_col_ind, float* point_range, int* start_ring_index, int* end_ring_index);
+
 // returns the number of extracted points
 int ro_image_projection(const void* raw, size_t n_points, int stride_bytes, int ring_offset_bytes, int n_scan, int horizon_scan,
                         int downsample_rate, float lidar_min_range, float lidar_max_range, float* range_image,
                         float* extracted_xyzi, int* point_col_ind, float* point_range, int* start_ring_index, int* end_ring_index) {
+  return ro_image_projection_deskew(raw, n_points, stride_bytes, ring_offset_bytes, n_scan, horizon_scan, downsample_rate, lidar_min_range,
+                                    lidar_max_range, 0, 0, nullptr, 0.1f, -1.0, range_image, extracted_xyzi, point_col_ind, point_range,
+                                    start_ring_index, end_ring_index);
+}
+
+int ro_image_projection_deskew(const void* raw, size_t n_points, int stride_bytes, int ring_offset_bytes, int n_scan, int horizon_scan,
+                               int downsample_rate, float lidar_min_range, float lidar_max_range, int deskew, int time_offset_bytes,
+                               const float* incre_rpy, float scan_period, double odom_time_diff, float* range_image,
+                               float* extracted_xyzi, int* point_col_ind, float* point_range, int* start_ring_index, int* end_ring_index) {
   const unsigned char* base = (const unsigned char*)raw;
   const size_t cells = (size_t)n_scan * horizon_scan;
   std::vector<float> full(cells * 4, 0.0f);
@@ -56,7 +84,12 @@ int ro_image_projection(const void* raw, size_t n_points, int stride_bytes, int 
     const size_t index = (size_t)columnIdn + (size_t)rowIdn * horizon_scan;
     if (range_image[index] != FLT_MAX) continue;                                  // :451 first writer wins
     range_image[index] = range;
-    full[index * 4 + 0] = x; full[index * 4 + 1] = y; full[index * 4 + 2] = z; full[index * 4 + 3] = intensity;
+    float dx = x, dy = y, dz = z;
+    if (deskew) {                                                                 // :454 thisPoint = deskewPoint(&thisPoint, relTime)
+      float rel; std::memcpy(&rel, base + i * stride_bytes + time_offset_bytes, sizeof(rel));
+      deskew_point(dx, dy, dz, (double)rel, incre_rpy, scan_period, odom_time_diff);
+    }
+    full[index * 4 + 0] = dx; full[index * 4 + 1] = dy; full[index * 4 + 2] = dz; full[index * 4 + 3] = intensity;
   }
   // imageProjection.cpp:477-505
   int count = 0;

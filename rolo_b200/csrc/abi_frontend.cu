@@ -8,6 +8,17 @@ extern "C" {
 // ------------------------------------------------------------------------------------------------
 // upstream range-image passes
 // ------------------------------------------------------------------------------------------------
+int rg_set_deskew(rg_ctx* c, const rg_deskew_params* p) {
+  CHECK_CTX(c);
+  if (!p) { c->fe_deskew.enabled = 0; return RG_OK; }
+  if (p->time_offset_bytes < 0 || p->time_offset_bytes % 4 || !(p->scan_period > 0.f) || p->odom_time_diff == 0.0)
+    return set_err(c, RG_ERR_INVALID, "rg_set_deskew: bad parameters");
+  c->fe_deskew.enabled = 1; c->fe_deskew.time_offset = p->time_offset_bytes;
+  c->fe_deskew.incre_rpy[0] = p->odom_incre_roll; c->fe_deskew.incre_rpy[1] = p->odom_incre_pitch; c->fe_deskew.incre_rpy[2] = p->odom_incre_yaw;
+  c->fe_deskew.scan_period = p->scan_period; c->fe_deskew.odom_time_diff = p->odom_time_diff;
+  return RG_OK;
+}
+
 static int fe_alloc(rg_ctx* c, int n_scan, int horizon) {
   const size_t cells = (size_t)n_scan * horizon;
   RG_CUDA(c, c->fe_owner.ensure(c->device, cells)); RG_CUDA(c, c->fe_range_image.ensure(c->device, cells));
@@ -30,13 +41,14 @@ int rg_image_projection(rg_ctx* c, const void* raw, size_t n_points, const rg_pr
   if (p->n_scan < 1 || p->horizon_scan < 1 || p->downsample_rate < 1 || p->point_stride_bytes < 12 || p->point_stride_bytes % 4 ||
       p->ring_offset_bytes < 0 || p->ring_offset_bytes + 2 > p->point_stride_bytes || n_points > (size_t)INT32_MAX / 2)
     return set_err(c, RG_ERR_INVALID, "rg_image_projection: bad parameters");
+  if (c->fe_deskew.enabled && c->fe_deskew.time_offset + 4 > p->point_stride_bytes) return set_err(c, RG_ERR_INVALID, "deskew: time offset outside the point record");
   if (int rc = fe_alloc(c, p->n_scan, p->horizon_scan)) return rc;
   const size_t cells = (size_t)p->n_scan * p->horizon_scan;
   RG_CUDA(c, c->fe_raw.ensure(c->device, std::max<size_t>(n_points * p->point_stride_bytes, 16)));
   if (n_points) RG_CUDA(c, cudaMemcpyAsync(c->fe_raw.p, raw, n_points * p->point_stride_bytes, cudaMemcpyHostToDevice, c->stream));
   ProjLaunch L;
   L.raw = c->fe_raw.p; L.n_points = (int)n_points; L.stride = p->point_stride_bytes; L.ring_offset = p->ring_offset_bytes;
-  L.n_scan = p->n_scan; L.horizon = p->horizon_scan; L.downsample = p->downsample_rate; L.min_range = p->lidar_min_range; L.max_range = p->lidar_max_range;
+  L.n_scan = p->n_scan; L.horizon = p->horizon_scan; L.downsample = p->downsample_rate; L.min_range = p->lidar_min_range; L.max_range = p->lidar_max_range; L.deskew = c->fe_deskew;
   L.owner = c->fe_owner.p; L.range_image = c->fe_range_image.p; L.full = c->fe_full.p; L.row_count = c->fe_row_count.p;
   L.extracted = c->fe_extracted.p; L.col_ind = c->fe_col.p; L.point_range = c->fe_prange.p; L.start_ring = c->fe_start.p; L.end_ring = c->fe_end.p;
   L.n_extracted = c->fe_counts.p;
@@ -120,6 +132,7 @@ extern "C" int rg_front_end_frame(rg_ctx* c, const void* raw, size_t n_points, c
       !(fp->surf_leaf_size > 0.f))
     return set_err(c, RG_ERR_INVALID, "rg_front_end_frame: bad parameters");
   if (pp->horizon_scan > FE_RING_CAP) return set_err(c, RG_ERR_UNSUPPORTED, "rg_front_end_frame: horizon_scan above the per-ring capacity (2048)");
+  if (c->fe_deskew.enabled && c->fe_deskew.time_offset + 4 > pp->point_stride_bytes) return set_err(c, RG_ERR_INVALID, "deskew: time offset outside the point record");
   if (int rc = fe_alloc(c, pp->n_scan, pp->horizon_scan)) return rc;
   const int cells = pp->n_scan * pp->horizon_scan;
   RG_CUDA(c, c->fe_raw.ensure(c->device, std::max<size_t>(n_points * pp->point_stride_bytes, 16)));
@@ -127,7 +140,7 @@ extern "C" int rg_front_end_frame(rg_ctx* c, const void* raw, size_t n_points, c
   RG_CUDA(c, cudaMemsetAsync(c->fe_counts.p, 0, 8 * sizeof(int), c->stream));
   ProjLaunch P;
   P.raw = c->fe_raw.p; P.n_points = (int)n_points; P.stride = pp->point_stride_bytes; P.ring_offset = pp->ring_offset_bytes;
-  P.n_scan = pp->n_scan; P.horizon = pp->horizon_scan; P.downsample = pp->downsample_rate; P.min_range = pp->lidar_min_range; P.max_range = pp->lidar_max_range;
+  P.n_scan = pp->n_scan; P.horizon = pp->horizon_scan; P.downsample = pp->downsample_rate; P.min_range = pp->lidar_min_range; P.max_range = pp->lidar_max_range; P.deskew = c->fe_deskew;
   P.owner = c->fe_owner.p; P.range_image = c->fe_range_image.p; P.full = c->fe_full.p; P.row_count = c->fe_row_count.p;
   P.extracted = c->fe_extracted.p; P.col_ind = c->fe_col.p; P.point_range = c->fe_prange.p; P.start_ring = c->fe_start.p; P.end_ring = c->fe_end.p;
   P.n_extracted = c->fe_counts.p;

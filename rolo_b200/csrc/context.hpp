@@ -223,6 +223,7 @@ struct rg_ctx {
   DevBuf<double> sc_out;
   sc::Manager sc_mgr;
   bool s2m_map_ok = false, s2m_scan_ok = false, s2m_lin_ok = false;
+  ProjDeskew fe_deskew = {0, 0, {0.f, 0.f, 0.f}, 0.1f, -1.0};
   DevBuf<unsigned char> fe_wire;        // packed PointXYZI records / uploaded message sections (cloud_info.hpp)
   bool fe_frame_ok = false;             // rg_front_end_frame products are resident
   int fe_n_scan = 0, fe_n[3] = {0, 0, 0};   // extracted, corner, surface counts of that frame

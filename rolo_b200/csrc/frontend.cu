@@ -1,6 +1,6 @@
 // frontend.cu — the two upstream range-image passes as sm_100a kernels.
 //
-//  ImageProjection::projectPointCloud + cloudExtraction   (src/imageProjection.cpp:399-505, deskew off)
+//  ImageProjection::projectPointCloud + cloudExtraction   (src/imageProjection.cpp:399-505, optional rotation-only deskewPoint :368-396)
 //  FeatureExtraction::calculateSmoothness / markOccludedPoints / extractFeatures
 //                                                          (src/featureExtraction.cpp:87-266)
 //  pcl::VoxelGrid<PointXYZI> per ring                      (call site featureExtraction.cpp:256-258)
@@ -69,15 +69,36 @@ __global__ void proj_claim_kernel(const unsigned char* __restrict__ raw, int n, 
   atomicMin(&owner[(size_t)row * horizon + col], i);      // first writer wins == smallest point index
 }
 
+// deskewPoint (imageProjection.cpp:368-396): rotate the point back by the odometry increment scaled to its time. sin / cos are
+// the correctly rounded float values (double libm rounded once), identical to the oracle's.
+__device__ __forceinline__ void deskew_point(float& x, float& y, float& z, float rel, const ProjDeskew& dk) {
+  const float ratio = (float)((double)rel / (double)dk.scan_period);              // :380 (relTime is a double parameter)
+  const float k = (float)((double)dk.scan_period / dk.odom_time_diff);            // Eigen takes the scalar as float (:383)
+  const float roll = -__fmul_rn(__fmul_rn(dk.incre_rpy[0], k), ratio), pitch = -__fmul_rn(__fmul_rn(dk.incre_rpy[1], k), ratio),
+              yaw = -__fmul_rn(__fmul_rn(dk.incre_rpy[2], k), ratio);
+  const float A = (float)cos((double)yaw), B = (float)sin((double)yaw), C = (float)cos((double)pitch), D = (float)sin((double)pitch),
+              E = (float)cos((double)roll), F = (float)sin((double)roll);
+  const float DE = __fmul_rn(D, E), DF = __fmul_rn(D, F);                         // pcl::getTransformation(0,0,0,roll,pitch,yaw)
+  const float t00 = __fmul_rn(A, C), t01 = __fsub_rn(__fmul_rn(A, DF), __fmul_rn(B, E)), t02 = __fadd_rn(__fmul_rn(B, F), __fmul_rn(A, DE));
+  const float t10 = __fmul_rn(B, C), t11 = __fadd_rn(__fmul_rn(A, E), __fmul_rn(B, DF)), t12 = __fsub_rn(__fmul_rn(B, DE), __fmul_rn(A, F));
+  const float t20 = -D, t21 = __fmul_rn(C, F), t22 = __fmul_rn(C, E);
+  const float nx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t00, x), __fmul_rn(t01, y)), __fmul_rn(t02, z)), 0.0f);
+  const float ny = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t10, x), __fmul_rn(t11, y)), __fmul_rn(t12, z)), 0.0f);
+  const float nz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(t20, x), __fmul_rn(t21, y)), __fmul_rn(t22, z)), 0.0f);
+  x = nx; y = ny; z = nz;
+}
+
 __global__ void proj_write_kernel(const unsigned char* __restrict__ raw, int stride, int ring_offset, const int* __restrict__ owner, int cells,
-                                  float* __restrict__ range_image, float4* __restrict__ full) {
+                                  ProjDeskew dk, float* __restrict__ range_image, float4* __restrict__ full) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cells) return;
   const int o = owner[c];
   if (o == INT_MAX) { range_image[c] = FLT_MAX; full[c] = make_float4(0.f, 0.f, 0.f, 0.f); return; }
   const RawPoint p = load_raw(raw, o, stride, ring_offset);
   range_image[c] = point_range(p.x, p.y, p.z);
-  full[c] = make_float4(p.x, p.y, p.z, __fmul_rn((float)p.ring, p.z));     // intensity := ring * z (:410)
+  float x = p.x, y = p.y, z = p.z;
+  if (dk.enabled) deskew_point(x, y, z, *reinterpret_cast<const float*>(raw + (size_t)o * stride + dk.time_offset), dk);   // :454
+  full[c] = make_float4(x, y, z, __fmul_rn((float)p.ring, p.z));           // intensity := ring * z of the raw point (:410)
 }
 
 __global__ void proj_count_kernel(const float* __restrict__ range_image, int horizon, int* row_count) {
@@ -405,7 +426,7 @@ cudaError_t launch_projection(const ProjLaunch& L, cudaStream_t stream) {
   if (L.n_points > 0)
     proj_claim_kernel<<<(L.n_points + 255) / 256, 256, 0, stream>>>(L.raw, L.n_points, L.stride, L.ring_offset, L.n_scan, L.horizon, L.downsample,
                                                                    L.min_range, L.max_range, L.owner);
-  proj_write_kernel<<<(cells + 255) / 256, 256, 0, stream>>>(L.raw, L.stride, L.ring_offset, L.owner, cells, L.range_image, L.full);
+  proj_write_kernel<<<(cells + 255) / 256, 256, 0, stream>>>(L.raw, L.stride, L.ring_offset, L.owner, cells, L.deskew, L.range_image, L.full);
   proj_count_kernel<<<L.n_scan, 256, 0, stream>>>(L.range_image, L.horizon, L.row_count);
   proj_extract_kernel<<<L.n_scan, 256, 0, stream>>>(L.range_image, L.full, L.row_count, L.n_scan, L.horizon, L.extracted, L.col_ind, L.point_range,
                                                     L.start_ring, L.end_ring, L.n_extracted);

@@ -8,11 +8,19 @@ constexpr int FE_MAX_CORNERS_PER_RING = 120;   // 6 sectors x 20 (featureExtract
 constexpr int FE_SECTOR_CAP = 2048;            // sortable sector length (horizon <= 12288)
 constexpr int FE_RING_CAP = 2048;              // surface candidates per ring (horizon <= 2048)
 
+struct ProjDeskew {             // deskewPoint (imageProjection.cpp:368-396), rotation only; enabled = deskewEnabled && odomAvailable
+  int enabled, time_offset;     // byte offset of the point's float relative time
+  float incre_rpy[3];           // odomIncreRoll / Pitch / Yaw
+  float scan_period;
+  double odom_time_diff;
+};
+
 struct ProjLaunch {
   const unsigned char* raw;   // device copy of the raw points
   int n_points, stride, ring_offset;
   int n_scan, horizon, downsample;
   float min_range, max_range;
+  ProjDeskew deskew;
   int* owner;                 // [n_scan*horizon] scratch: smallest point index claiming the cell
   float* range_image;         // [n_scan*horizon]
   float4* full;               // [n_scan*horizon] xyz + intensity

@@ -43,6 +43,14 @@ class FrontEnd:
         except Exception:
             pass
 
+    def set_deskew(self, incre_rpy=None, scan_period: float = 0.1, odom_time_diff: float = 0.1, time_offset: int = 24):
+        """deskewPoint (imageProjection.cpp:368-396): rotation-only correction by the odometry increment; None disables it."""
+        if incre_rpy is None:
+            capi.check(self.L.rg_set_deskew(self.h, None), self.h)
+            return
+        p = capi.DeskewParams(time_offset, float(incre_rpy[0]), float(incre_rpy[1]), float(incre_rpy[2]), scan_period, odom_time_diff)
+        capi.check(self.L.rg_set_deskew(self.h, C.byref(p)), self.h)
+
     def image_projection(self, raw: np.ndarray) -> dict:
         raw = np.ascontiguousarray(raw)
         assert raw.dtype.itemsize == self.pp.point_stride_bytes

@@ -80,3 +80,23 @@ def test_streamed_front_end_matches_oracle_chain():
             assert drot <= 1e-4 and np.max(np.abs(t - to)) <= 1e-4
             assert r.nrIterations() == o.nrIterations()
         prev = cur
+
+
+def test_deskew_matches_oracle():
+    """deskewPoint (imageProjection.cpp:368-396) with deskewEnabled && odomAvailable: rotated points bit-equal to the oracle,
+    range image / columns unchanged (they are computed before the correction)."""
+    scene = synth.make_scene()
+    raw = synth.raw_frame(scene, synth.pose((1.0, -2.0, 30.0), (1.0, 0.5, 0.0)), "vlp64", extra=500)
+    dk = {"time_offset": 24, "incre_rpy": np.array([0.004, -0.007, 0.031], np.float32), "scan_period": 0.1, "odom_time_diff": 0.0987}
+    fe = FrontEnd(n_scan=64, horizon_scan=1024)
+    plain = fe.image_projection(raw)
+    fe.set_deskew(dk["incre_rpy"], dk["scan_period"], dk["odom_time_diff"], dk["time_offset"])
+    pg = fe.image_projection(raw)
+    po = ob.image_projection(raw, 64, 1024, deskew=dk)
+    for k in ("range_image", "extracted", "point_col_ind", "point_range", "start_ring_index", "end_ring_index"):
+        assert np.array_equal(pg[k], po[k]), k
+    assert np.array_equal(pg["range_image"], plain["range_image"]) and np.array_equal(pg["extracted"][:, 3], plain["extracted"][:, 3])
+    moved = np.linalg.norm(pg["extracted"][:, :3] - plain["extracted"][:, :3], axis=1)
+    assert moved.max() > 0.05 and np.allclose(np.linalg.norm(pg["extracted"][:, :3], axis=1), np.linalg.norm(plain["extracted"][:, :3], axis=1), rtol=1e-5)
+    fe.set_deskew(None)
+    assert np.array_equal(fe.image_projection(raw)["extracted"], plain["extracted"])
