@@ -75,11 +75,19 @@ __global__ void morton_kernel(const float4* __restrict__ pts, int n, const int* 
   idx[i] = i;
 }
 
-__global__ void gather_sorted_kernel(const float4* __restrict__ pts, const int* __restrict__ idx, int n, float4* __restrict__ sorted) {
+// Morton-ordered copy of the points (w = original index) + the packed cell coordinates (ix | iy << 21 | iz << 42) of each
+// sorted point: the kNN kernel needs them per query, and de-interleaving the code there would cost ~100 warp-instructions
+// per query instead of ~100 per 32 points here. `cells` reuses the unsorted-code buffer, which is dead after the sort.
+__global__ void gather_sorted_kernel(const float4* __restrict__ pts, const int* __restrict__ idx, int n, const int* __restrict__ bbox,
+                                     float4* __restrict__ sorted, unsigned long long* __restrict__ cells) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const int i = idx[j];
   float4 p = pts[i];
+  const Quant q = make_quant(bbox);
+  unsigned ix, iy, iz;
+  quantize(q, p.x, p.y, p.z, ix, iy, iz);          // identical to morton_kernel's
+  cells[j] = (unsigned long long)ix | ((unsigned long long)iy << 21) | ((unsigned long long)iz << 42);
   p.w = __int_as_float(i);
   sorted[j] = p;
 }
@@ -209,8 +217,8 @@ __global__ void bucket_table_kernel(const unsigned long long* __restrict__ codes
 }
 
 __global__ void __launch_bounds__(256, 5)        // 48 registers: 40 warps/SM measured 4 % faster than 32
-knn_warp_kernel(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes, const int* __restrict__ bucket_start,
-                int n, int k, const int* __restrict__ bbox, int* __restrict__ knn_out) {
+knn_warp_kernel(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes, const unsigned long long* __restrict__ cells,
+                const int* __restrict__ bucket_start, int n, int k, const int* __restrict__ bbox, int* __restrict__ knn_out) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -226,7 +234,8 @@ knn_warp_kernel(const float4* __restrict__ sorted, const unsigned long long* __r
     const float4 q = __ldg(sorted + j);
     const int self = __float_as_int(q.w);
     const unsigned long long cq = __ldg(codes + j);
-    const unsigned ix = compact21(cq), iy = compact21(cq >> 1), iz = compact21(cq >> 2);
+    const unsigned long long cc3 = __ldg(cells + j);
+    const unsigned ix = (unsigned)(cc3 & 0x1FFFFFull), iy = (unsigned)((cc3 >> 21) & 0x1FFFFFull), iz = (unsigned)(cc3 >> 42);
 
     // start level: reuse the previous query's final level when this query lies in the same cell there; otherwise
     // the level-cpl(code[j], code[j-4]) cell holds the sorted entries j-4..j (likewise on the right), so the
@@ -552,7 +561,7 @@ cudaError_t launch_sort_cloud(const float4* pts, int n, const CovScratch& s, boo
   size_t temp = s.cub_temp_bytes;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(s.cub_temp, temp, s.codes_in, s.codes_out, s.idx_in, s.idx_out, n, 0, 3 * MORTON_BITS, stream);
   if (e != cudaSuccess) return e;
-  gather_sorted_kernel<<<nb, tb, 0, stream>>>(pts, s.idx_out, n, s.sorted);
+  gather_sorted_kernel<<<nb, tb, 0, stream>>>(pts, s.idx_out, n, s.bbox, s.sorted, s.codes_in);   // codes_in now holds the packed cell coordinates
   if (bucket_table) bucket_table_kernel<<<(N_BUCKETS + 1 + tb - 1) / tb, tb, 0, stream>>>(s.codes_out, n, s.bucket_start);
   return cudaGetLastError();
 }
@@ -573,7 +582,7 @@ cudaError_t launch_covariances(const CovLaunch& L, cudaStream_t stream) {
   if (L.k <= 32) {
     const int queries_per_block = (256 / 32) * KNN_QPW;
     const int gb = (n + queries_per_block - 1) / queries_per_block;
-    knn_warp_kernel<<<gb, 256, 0, stream>>>(L.s.sorted, L.s.codes_out, L.s.bucket_start, n, L.k, L.s.bbox, L.knn);
+    knn_warp_kernel<<<gb, 256, 0, stream>>>(L.s.sorted, L.s.codes_out, L.s.codes_in, L.s.bucket_start, n, L.k, L.s.bbox, L.knn);
   } else {
     knn_thread_kernel<<<(n + 127) / 128, 128, 0, stream>>>(L.s.sorted, L.s.codes_out, n, L.k, L.s.bbox, L.knn);
   }

@@ -5,7 +5,7 @@
 namespace rolo {
 
 struct CovScratch {           // all device pointers; sized for n points (see cov_scratch_bytes)
-  unsigned long long* codes_in;   // [n]
+  unsigned long long* codes_in;   // [n] unsorted codes; after the sort: packed cell coordinates of the sorted points
   unsigned long long* codes_out;  // [n]
   int* idx_in;                    // [n]
   int* idx_out;                   // [n]
