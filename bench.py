@@ -176,7 +176,7 @@ def run_reference(args, rank, world):
                          "sample": f"{args.steps} full registrations (1 per step) after {args.warmup} warm-ups"},
         "e2e": {"value": val, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline_sample(clouds_host):
@@ -202,7 +202,30 @@ def cpu_baseline_sample(clouds_host):
             "sample": f"{n} full 128x2048 registrations (covariances + voxel map + {GN_ITERS} GN iters), {dt:.1f} s of CPU work"}, poses
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout. Native libraries print there too (NCCL's version banner goes to stdout whatever
+    NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to the
+    original stdout at the end."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    while data:
+        data = data[os.write(fd, data):]
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -231,8 +254,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
 
     P = args.pairs
@@ -348,7 +369,7 @@ def main():
         "clocks": clocks,
         "parity": {"max_rot_rad_vs_gt": max_rot, "max_trans_m_vs_gt": max_tr, **(cpu_parity or {})},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
