@@ -89,3 +89,55 @@ def test_oracle_recovers_the_pose_on_a_synthetic_map():
     # too few features: the reference only warns and leaves the pose alone (backMapping.cpp:687,705-707)
     few = o.optimize(case["pose_guess"], edge_min=10 ** 6)
     assert few["iterations"] == -1 and np.array_equal(few["pose"], case["pose_guess"])
+
+
+def _rot(tf):
+    return synth.pose6_matrix(np.asarray(tf, dtype=np.float64))
+
+
+def test_coefficients_and_jacobian_have_their_geometric_meaning():
+    """Independent (numpy, float64) reading of what the restated formulas must mean: a surface coefficient is s x (unit normal of
+    the plane through the five neighbours, signed distance); a corner coefficient is s x (unit vector from the line to the point,
+    distance to the line); the rows of matA are the derivatives of the residual with respect to (roll, pitch, yaw, x, y, z)."""
+    case = synth.scan2map_case(helpers.oracle_features(32, 512), "small")
+    o = ob.Scan2Map(); o.setMap(case["map_corner"], case["map_surf"]); o.setScan(case["scan_corner"], case["scan_surf"])
+    tf = case["pose_guess"].astype(np.float64)
+    lin = o.linearize(case["pose_guess"])
+    T = _rot(tf)
+    # --- surfaces
+    P = case["scan_surf"][:, :3].astype(np.float64); W = P @ T[:3, :3].T + T[:3, 3]
+    M = case["map_surf"][:, :3].astype(np.float64)
+    sel = np.flatnonzero(lin["flag_surf"])[:300]
+    for i in sel:
+        d = np.sum((M - W[i]) ** 2, axis=1); nn = np.argsort(d, kind="stable")[:5]
+        n = np.linalg.lstsq(M[nn], -np.ones(5), rcond=None)[0]; nrm = np.linalg.norm(n); n, dd = n / nrm, 1.0 / nrm
+        pd2 = n @ W[i] + dd
+        s = 1 - 0.9 * abs(pd2) / np.sqrt(np.linalg.norm(P[i]))
+        c = lin["coeff_surf"][i].astype(np.float64)
+        assert np.allclose(c[:3], s * n, atol=2e-3) and abs(c[3] - s * pd2) < 2e-3
+    # --- corners
+    P = case["scan_corner"][:, :3].astype(np.float64); Wc = P @ T[:3, :3].T + T[:3, 3]
+    Mc = case["map_corner"][:, :3].astype(np.float64)
+    selc = np.flatnonzero(lin["flag_corner"])[:100]
+    assert selc.size > 20
+    for i in selc:
+        d = np.sum((Mc - Wc[i]) ** 2, axis=1); nn = np.argsort(d, kind="stable")[:5]
+        ctr = Mc[nn].mean(axis=0); w, v = np.linalg.eigh(np.cov((Mc[nn] - ctr).T, bias=True)); u = v[:, 2]
+        r = Wc[i] - ctr; perp = r - (r @ u) * u; dist = np.linalg.norm(perp)
+        s = 1 - 0.9 * dist
+        c = lin["coeff_corner"][i].astype(np.float64)
+        assert abs(c[3] - s * dist) < 2e-3 and np.allclose(c[:3], s * perp / dist, atol=5e-3)
+    # --- Jacobian rows by central differences of r(tf) = c . (R(tf) p + t(tf)) -> AtA, AtB
+    rows = []; res = []
+    for pts, cf, fl in ((case["scan_corner"], lin["coeff_corner"], lin["flag_corner"]), (case["scan_surf"], lin["coeff_surf"], lin["flag_surf"])):
+        idx = np.flatnonzero(fl); p = pts[idx, :3].astype(np.float64); c = cf[idx].astype(np.float64)
+        J = np.zeros((idx.size, 6))
+        for k in range(6):
+            h = 1e-6; tp = tf.copy(); tm = tf.copy(); tp[k] += h; tm[k] -= h
+            Tp, Tm = _rot(tp), _rot(tm)
+            J[:, k] = np.sum(c[:, :3] * ((p @ Tp[:3, :3].T + Tp[:3, 3]) - (p @ Tm[:3, :3].T + Tm[:3, 3])), axis=1) / (2 * h)
+        rows.append(J); res.append(-c[:, 3])
+    J = np.vstack(rows); b = np.concatenate(res)
+    AtA, AtB = J.T @ J, J.T @ b
+    assert np.allclose(lin["AtA"], AtA, rtol=2e-3, atol=2e-3 * np.abs(AtA).max())
+    assert np.allclose(lin["AtB"], AtB, rtol=2e-3, atol=2e-3 * np.abs(AtB).max())
