@@ -401,6 +401,51 @@ class SCManager:
         return lid, yaw.value
 
 
+_REF_SC_PATH = os.path.join(_HERE, "_ref", "librolo_ref_sc.so")
+
+
+def ref_sc_available() -> bool:
+    return os.path.exists(_REF_SC_PATH)
+
+
+class RefSCManager:
+    """The REFERENCE's own SCManager (src/scancontext/Scancontext.cpp compiled from /root/reference with its vendored nanoflann,
+    oracle/ref_sc_driver.cpp); same surface as SCManager above. Only for pinning the restated oracle."""
+
+    def __init__(self):
+        self.L = C.CDLL(_REF_SC_PATH)
+        self.L.rsc_create.restype = C.c_void_p
+        self.h = C.c_void_p(self.L.rsc_create())
+
+    def __del__(self):
+        try:
+            self.L.rsc_destroy(self.h)
+        except Exception:
+            pass
+
+    def makeAndSaveScancontextAndKeys(self, scan):
+        a = np.ascontiguousarray(scan, dtype=np.float32)
+        self.L.rsc_make_and_save(self.h, C.c_void_p(a.ctypes.data), C.c_size_t(a.shape[0]), C.c_size_t(a.shape[1]))
+
+    def size(self): return self.L.rsc_size(self.h)
+
+    def get(self, index=-1):
+        d = np.empty((20, 60), np.float64); rk = np.empty(20, np.float64); sk = np.empty(60, np.float64)
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+        assert self.L.rsc_get(self.h, index, vp(d), vp(rk), vp(sk)) == 0
+        return d, rk, sk
+
+    def distanceBtnScanContext(self, i, j):
+        d = C.c_double(); s = C.c_int()
+        assert self.L.rsc_distance(self.h, i, j, C.byref(d), C.byref(s)) == 0
+        return d.value, s.value
+
+    def detectLoopClosureID(self):
+        yaw = C.c_float()
+        lid = self.L.rsc_detect(self.h, C.byref(yaw))
+        return lid, yaw.value
+
+
 # ---- oracle/_ref: the REFERENCE's own rot_gicp sources compiled against oracle/ref_shim (see oracle/Makefile) ----
 _REF_PATH = os.path.join(_HERE, "_ref", "librolo_ref.so")
 _ref = None

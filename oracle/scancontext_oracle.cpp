@@ -6,10 +6,12 @@
  *   makeSectorkeyFromScancontext :214-227, makeAndSaveScancontextAndKeys :236-250, detectLoopClosureID :253-344.
  * Matrices are Eigen::MatrixXd in the reference; here plain row-major [ring][sector] doubles.
  *
- * PARITY UNPINNED: the reference has no test for this code, and it leans on third-party pieces absent from /root/reference
- * whose last-bit behaviour is theirs: Eigen's vectorised norm()/dot()/mean() reductions (restated as in-order sums),
- * nanoflann's kd-tree 3-NN over the float ring keys (restated as an exact search under (float distance, index) order) and
- * libm's atan(float) (restated as the correctly rounded value: double atan rounded to float — what glibc >= 2.41 returns).
+ * PINNING: the reference has no test for this code, but the code itself compiles here: oracle/_ref/librolo_ref_sc.so is the
+ * reference's own Scancontext.cpp with its vendored nanoflann kd-tree, built from /root/reference against oracle/ref_shim
+ * (`make -C oracle ref`, oracle/ref_sc_driver.cpp), and tests/test_scancontext_vs_ref_cpu.py requires descriptors, keys,
+ * distances / shifts and loop detections of this restatement to EQUAL it (they do, bit for bit, on 45-frame sequences).
+ * What stays restated: Eigen's vectorised norm()/dot()/mean() reductions (in-order sums in ref_shim/Eigen/Dense and here)
+ * and libm's atan(float), here the correctly rounded value (double atan rounded to float) so that the GPU can reproduce it.
  */
 #include <algorithm>
 #include <cmath>
