@@ -10,12 +10,15 @@
  * All arithmetic is float like the reference's (PointType = pcl::PointXYZI, cv::Mat CV_32F); AtA/AtB are accumulated in
  * double and rounded to float (cv::gemm's working type for CV_32F is double).
  *
- * PARITY UNPINNED: the reference has no test or golden vector for this path, and the numerics it calls live in third-party
- * code that is absent from /root/reference (README.md:28-33, unpinned): pcl::getTransformation and pcl::KdTreeFLANN
- * (PCL >= 1.10), cv::eigen / cv::solve(DECOMP_QR) / cv::Mat::inv (OpenCV >= 4.2), Eigen::colPivHouseholderQr (Eigen >= 3.3.7).
- * Their published algorithms are restated below (each function says which): getTransformation's closed form, exact kNN
- * under (float distance, index) order, OpenCV's classical max-pivot Jacobi with descending sort, Householder QR
- * (column-pivoted for the 5x3 plane fit), LU with partial pivoting. Compiled with -ffp-contract=off.
+ * PINNING (partial): the reference has no test or golden vector for this path and backMapping.cpp cannot be compiled here
+ * (ROS, GTSAM, PCL, OpenCV C++ are absent), so the path as a whole is PARITY UNPINNED. Its third-party numerics are pinned
+ * where the real library exists in the image: the restated cv::eigen (3x3 and 6x6) and cv::Mat::inv are BIT-EQUAL to OpenCV
+ * 4.13 (python cv2; golden vectors tests/golden/opencv_s2m_golden.npz from tools/make_opencv_golden.py, plus a live check);
+ * cv::solve(DECOMP_QR) agrees to rounding only (that build dispatches to LAPACK). Still restated from their published
+ * algorithms: pcl::getTransformation's closed form (checked against scipy), exact kNN under (float distance, index) order,
+ * Eigen::colPivHouseholderQr (checked against numpy lstsq), cv::gemm's double accumulation. The transcription of the
+ * reference's own formulas (coefficients, LOAM Jacobian) is checked against their geometric meaning and finite differences
+ * in tests/test_scan2map_cpu.py. Compiled with -ffp-contract=off.
  */
 #include <omp.h>
 

@@ -141,3 +141,39 @@ def test_coefficients_and_jacobian_have_their_geometric_meaning():
     AtA, AtB = J.T @ J, J.T @ b
     assert np.allclose(lin["AtA"], AtA, rtol=2e-3, atol=2e-3 * np.abs(AtA).max())
     assert np.allclose(lin["AtB"], AtB, rtol=2e-3, atol=2e-3 * np.abs(AtB).max())
+
+
+def test_restated_opencv_routines_against_real_opencv_golden_vectors():
+    """tests/golden/opencv_s2m_golden.npz holds outputs of the real OpenCV (tools/make_opencv_golden.py, the image's cv2 4.13):
+    the restated cv::eigen (3x3, 6x6) and cv::Mat::inv are BIT-EQUAL to it; cv::solve(DECOMP_QR) dispatches to LAPACK in that
+    build, so the Householder restatement agrees to rounding (1e-5 relative on these well-conditioned systems)."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), "golden", "opencv_s2m_golden.npz"))
+    L = ob.lib(); P = capi.load()
+    for n in (3, 6):
+        for A, W, V in zip(G[f"eig{n}_A"], G[f"eig{n}_W"], G[f"eig{n}_V"]):
+            A = np.ascontiguousarray(A)
+            for fn in (L.ro_s2m_eigen, P.rgt_s2m_eigen):                      # oracle and product host code
+                w = np.empty(n, np.float32); v = np.empty((n, n), np.float32)
+                fn(n, vp(A), vp(w), vp(v))
+                assert np.array_equal(w, W) and np.array_equal(v, V)
+    for M, I in zip(G["inv_M"], G["inv_I"]):
+        M = np.ascontiguousarray(M); inv = np.empty((6, 6), np.float32)
+        assert L.ro_s2m_invert(6, vp(M), vp(inv)) == 1 and np.array_equal(inv, I)
+        assert P.rgt_s2m_invert6(vp(M), vp(inv)) == 1 and np.array_equal(inv, I)
+    for A, b, x in zip(G["qr_A"], G["qr_b"], G["qr_x"]):
+        A = np.ascontiguousarray(A); b = np.ascontiguousarray(b); xo = np.empty(6, np.float32)
+        L.ro_s2m_qr_solve(6, 6, vp(A), vp(b), vp(xo), 0)
+        assert np.max(np.abs(xo - x)) <= 1e-5 * np.max(np.abs(x))
+
+
+def test_restated_opencv_routines_against_live_opencv():
+    cv2 = pytest.importorskip("cv2")
+    L = ob.lib()
+    g = np.random.default_rng(77)
+    for _ in range(100):
+        P5 = (g.standard_normal((5, 3)) * g.uniform(0.05, 2.0)).astype(np.float32); P5 -= P5.mean(0)
+        A = (P5.T @ P5 / 5).astype(np.float32); A = ((A + A.T) / 2).astype(np.float32)
+        w = np.empty(3, np.float32); v = np.empty((3, 3), np.float32); L.ro_s2m_eigen(3, vp(A), vp(w), vp(v))
+        ok, wc, vc = cv2.eigen(A)
+        assert np.array_equal(w, wc.reshape(-1)) and np.array_equal(v, vc)
