@@ -1,5 +1,5 @@
 // scan2map.cu — backMapping's cornerOptimization + surfOptimization + combineOptimizationCoeffs + the matA/matB assembly of
-// LMOptimization (src/backMapping.cpp:719-1006) as ONE kernel per Gauss-Newton iteration.
+// LMOptimization (src/backMapping.cpp:719-1006): two kernels per Gauss-Newton iteration.
 //
 // Reference: per scan feature point, transform to the map frame, kd-tree 5-NN in the corner / surface map, accept when the
 // 5th neighbour is closer than 1 m, then either a PCA line test + point-to-line coefficient (corners, cv::eigen) or a plane
@@ -19,8 +19,8 @@
 //   * no compaction: unselected points contribute zero rows; the 21 + 6 + 1 sums (AtA upper triangle, AtB, count) are
 //     formed in double: warp shuffle tree -> block -> per-block partial -> the last block adds the partials in block
 //     order, so the result is deterministic.
-// HBM traffic is a few hundred KB per iteration (the maps are L2-resident); the kernel is latency / instruction bound and
-// sized as a persistent grid over the scan points.
+// HBM traffic is a few MB per iteration (the maps are L2-resident): the 5-NN kernel is instruction-issue bound, the fit kernel
+// latency bound (profiles/r01_ncu_s2m_v2.txt).
 
 #include "scan2map.cuh"
 #include "morton.cuh"
