@@ -62,3 +62,13 @@ def test_product_never_imports_the_oracle():
                 assert not bad.search(txt), os.path.join(dirpath, f)
     out = subprocess.run(["ldd", capi.lib_path()], capture_output=True, text=True).stdout
     assert "oracle" not in out
+
+
+def test_c_examples_compile_and_link_as_plain_c(tmp_path):
+    """Both examples are C99 against include/rolo_gicp.h only (no GPU needed to compile and link)."""
+    import subprocess
+    libdir = os.path.dirname(capi.lib_path())
+    capi.load()
+    for name in ("lidar_odometry_sequence", "back_end_sequence"):
+        subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", name + ".c"),
+                               "-o", str(tmp_path / name), "-L", libdir, "-lrolo_gicp_b200", f"-Wl,-rpath,{libdir}", "-lm"])
