@@ -66,6 +66,31 @@ int main(int argc,char**argv){
       for(int t=0;t<27;t++){int o=order_[t];for(int c=lo[o];c<lo[o]+cnt[o];c++){float dx=q.x-pts[c].x,dy=q.y-pts[c].y,dz=q.z-pts[c].z;float d=dx*dx;d=d+dy*dy;d=d+dz*dz;uint32_t db;memcpy(&db,&d,4);keys.push_back(((u64)db<<32)|(unsigned)pts[c].id);}}
       std::vector<u64> top(32,0x7F7FFFFF7FFFFFFFull);
       int THR=(variant&8)?10:6;
+      if(variant&32){
+        // window-first: the 32 sorted-order neighbours of the query form the first batch (one contiguous load, no cell mapping)
+        int w0=std::max(0,std::min(j-16,n-32)), w1=std::min(n,w0+32);
+        std::vector<u64> wk;
+        for(int c=w0;c<w1;c++){float dx=q.x-pts[c].x,dy=q.y-pts[c].y,dz=q.z-pts[c].z;float d=dx*dx;d=d+dy*dy;d=d+dz*dz;uint32_t db;memcpy(&db,&d,4);wk.push_back(((u64)db<<32)|(unsigned)pts[c].id);}
+        n_first++; n_batches+=0.6;   // cheaper batch: no owner search
+        for(u64 k2:wk)top.push_back(k2);std::sort(top.begin(),top.end());top.resize(32);
+        // block scan, skipping candidates whose sorted position lies inside the window
+        std::vector<u64> keys2; int t=0;
+        static const int order2[27]={13,0,1,2,3,4,5,6,7,8,9,10,11,12,14,15,16,17,18,19,20,21,22,23,24,25,26};
+        for(size_t base=0;base<keys.size();base+=32){
+          n_batches++;
+          u64 kth=top[K-1];int pass=0;std::vector<u64>pk;
+          for(size_t g=base;g<std::min(base+32,keys.size());g++){
+            // recover sorted position of candidate g
+            int rem=(int)g,pos=-1;for(int tt=0;tt<27;tt++){int o=order2[tt];if(rem<cnt[o]){pos=lo[o]+rem;break;}rem-=cnt[o];}
+            if(pos>=w0&&pos<w1)continue;
+            if(keys[g]<kth){pass++;pk.push_back(keys[g]);}
+          }
+          if(!pass)continue;
+          if(pass>THR)n_sorts++;else n_inserts+=pass;
+          for(u64 k2:pk)top.push_back(k2);std::sort(top.begin(),top.end());top.resize(32);
+        }
+        (void)t;
+      } else
       if(!(variant&4)){
       for(size_t base=0;base<keys.size();base+=32){
         n_batches++;
