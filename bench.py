@@ -274,14 +274,14 @@ def main():
     ext = torch.cuda.ExternalStream(batch.stream(), device=dev)
 
     def step(resident: bool):
-        # per pair: install both clouds, then start the covariance estimation right away (it is part of align();
-        # starting it as soon as a pair's clouds are queued lets uploads and kNN kernels of different pairs overlap)
+        # per pair: install both clouds (host path: asynchronous H2D copies on the batch's upload streams); align() then
+        # estimates the covariances of all clouds in groups of 32 pairs per launch chain (each group waits only for its
+        # own uploads), builds every voxel map in one launch chain and iterates the pairs in lock step
         for i in range(P):
             if resident:
                 batch[i].setInputTarget(tgt_dev[i]); batch[i].setInputSource(src_dev[i])
             else:
                 batch[i].setInputTarget(tgt_host[i]); batch[i].setInputSource(src_host[i])
-            batch[i].calculate_covariances(capi.TARGET); batch[i].calculate_covariances(capi.SOURCE)
         return batch.align()
 
     def barrier():

@@ -5,6 +5,7 @@
 // B200-class device is usable; there is no CPU fallback anywhere in this library.
 
 #include "context.hpp"
+#include <limits>
 
 std::mutex g_mutex;
 std::atomic<unsigned long long> g_launches{0};
@@ -134,7 +135,10 @@ int upload_cloud(rg_ctx* c, Cloud& cl, const float* host, size_t n, size_t strid
   RG_CUDA(c, cudaGetLastError());
   if (us != c->stream) {
     RG_CUDA(c, cudaEventRecord(c->ev_upload, us));
-    RG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_upload, 0));
+    // inside a batch the shared batch stream is NOT made to wait here: rg_batch_align joins the uploads group by group
+    // (and use_device() joins lazily for any other call), so later pairs' copies overlap earlier pairs' kernels
+    if (c->batch) c->side_pending = true;
+    else RG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_upload, 0));
   }
   return RG_OK;
 }
@@ -160,32 +164,79 @@ int upload_cloud_device(rg_ctx* c, Cloud& cl, const float* dev, size_t n, cudaSt
   return RG_OK;
 }
 
-int calc_cov(rg_ctx* c, Cloud& cl) {
-  if (use_device(c)) return RG_ERR_CUDA;
-  if (cl.n == 0) return set_err(c, RG_ERR_INVALID, "calculate_covariances: empty cloud");
+// RotVGICP::calculate_covariances (rot_vgicp_impl.hpp:421-496) of a GROUP of clouds (one launch chain for all of them) on `stream`,
+// with the scratch `bufs`. knn_out (optional, single cloud only) receives the unordered neighbour sets.
+int calc_cov_group(rg_ctx* c, const std::vector<Cloud*>& clouds, KnnBufs& bufs, cudaStream_t stream, int* knn_out = nullptr) {
+  if (clouds.empty()) return RG_OK;
   if (c->regularization_method < RG_REG_NONE || c->regularization_method > RG_REG_PLANE_S)
     return set_err(c, RG_ERR_UNSUPPORTED, "here must not be reached (unknown regularization method; reference abort()s, rot_vgicp_impl.hpp:472-474)");
-  if (c->k_correspondences < 1 || c->k_correspondences > 64) return set_err(c, RG_ERR_INVALID, "k_correspondences must be in [1,64]");
-  if (cl.n < c->k_correspondences)
-    return set_err(c, RG_ERR_INVALID, "cloud has fewer points than k_correspondences (reference reads uninitialised neighbours here, rot_vgicp_impl.hpp:438-444)");
-  const int n = cl.n;
-  RG_CUDA(c, c->codes_in.ensure(c->device, n)); RG_CUDA(c, c->codes_out.ensure(c->device, n));
-  RG_CUDA(c, c->idx_in.ensure(c->device, n)); RG_CUDA(c, c->idx_out.ensure(c->device, n));
-  RG_CUDA(c, c->sorted.ensure(c->device, n)); RG_CUDA(c, c->bbox.ensure(c->device, 8)); RG_CUDA(c, c->bucket_start.ensure(c->device, cov_bucket_table_entries()));
-  const size_t tb = cov_cub_temp_bytes(n);
-  RG_CUDA(c, c->cub_temp.ensure(c->device, tb));
-  RG_CUDA(c, c->knn_idx.ensure(c->device, (size_t)n * c->k_correspondences));
-  CovLaunch L;
-  L.pts = cl.pts.p; L.n = n; L.k = c->k_correspondences; L.method = c->regularization_method;
-  L.cov6 = cl.cov6.p; L.knn = c->knn_idx.p;
-  L.s.codes_in = c->codes_in.p; L.s.codes_out = c->codes_out.p; L.s.idx_in = c->idx_in.p; L.s.idx_out = c->idx_out.p;
-  L.s.sorted = c->sorted.p; L.s.cub_temp = c->cub_temp.p; L.s.cub_temp_bytes = tb; L.s.bbox = c->bbox.p; L.s.bucket_start = c->bucket_start.p;
-  // zero the padding rows of the covariance tiles (only the last tile has any)
-  if (cl.n_pad > n) RG_CUDA(c, cudaMemsetAsync(cl.cov6.p + (size_t)(cl.n_pad / TILE_PTS - 1) * COV_PLANES * TILE_PTS, 0, sizeof(float) * COV_PLANES * TILE_PTS, c->stream));
-  RG_CUDA(c, launch_covariances(L, c->stream));
-  g_launches += 7;   // bbox_init, bbox, morton, gather, bucket table, knn, cov (cub's radix-sort kernels not counted)
-  cl.has_cov = true;
+  const int k = c->k_correspondences;
+  if (k < 1 || k > 64) return set_err(c, RG_ERR_INVALID, "k_correspondences must be in [1,64]");
+  size_t total = 0; int max_n = 0;
+  for (Cloud* cl : clouds) {
+    if (cl->n == 0) return set_err(c, RG_ERR_INVALID, "calculate_covariances: empty cloud");
+    if (cl->n < k)
+      return set_err(c, RG_ERR_INVALID, "cloud has fewer points than k_correspondences (reference reads uninitialised neighbours here, rot_vgicp_impl.hpp:438-444)");
+    total += (size_t)cl->n; max_n = std::max(max_n, cl->n);
+  }
+  if (total > (size_t)1 << 30) return set_err(c, RG_ERR_INVALID, "calculate_covariances: group too large");
+  // zero the padding rows of the covariance tiles (only the last tile of a cloud has any)
+  for (Cloud* cl : clouds)
+    if (cl->n_pad > cl->n) RG_CUDA(c, cudaMemsetAsync(cl->cov6.p + (size_t)(cl->n_pad / TILE_PTS - 1) * COV_PLANES * TILE_PTS, 0, sizeof(float) * COV_PLANES * TILE_PTS, stream));
+  if (k > 32) {   // generic path: thread-per-query search into explicit neighbour lists, one cloud at a time
+    for (Cloud* cl : clouds) {
+      const int n = cl->n;
+      RG_CUDA(c, c->codes_in.ensure(c->device, n)); RG_CUDA(c, c->codes_out.ensure(c->device, n));
+      RG_CUDA(c, c->idx_in.ensure(c->device, n)); RG_CUDA(c, c->idx_out.ensure(c->device, n));
+      RG_CUDA(c, c->sorted.ensure(c->device, n)); RG_CUDA(c, c->bbox.ensure(c->device, 8)); RG_CUDA(c, c->bucket_start.ensure(c->device, cov_bucket_table_entries()));
+      const size_t tb = cov_cub_temp_bytes(n);
+      RG_CUDA(c, c->cub_temp.ensure(c->device, tb));
+      RG_CUDA(c, c->knn_idx.ensure(c->device, (size_t)n * k));
+      CovLaunch L;
+      L.pts = cl->pts.p; L.n = n; L.k = k; L.method = c->regularization_method;
+      L.cov6 = cl->cov6.p; L.knn = c->knn_idx.p;
+      L.s.codes_in = c->codes_in.p; L.s.codes_out = c->codes_out.p; L.s.idx_in = c->idx_in.p; L.s.idx_out = c->idx_out.p;
+      L.s.sorted = c->sorted.p; L.s.cub_temp = c->cub_temp.p; L.s.cub_temp_bytes = tb; L.s.bbox = c->bbox.p; L.s.bucket_start = c->bucket_start.p;
+      RG_CUDA(c, launch_covariances_generic(L, stream));
+      g_launches += 6;
+      if (knn_out) RG_CUDA(c, cudaMemcpyAsync(knn_out, c->knn_idx.p, sizeof(int) * (size_t)n * k, cudaMemcpyDeviceToDevice, stream));
+      cl->has_cov = true;
+    }
+    return RG_OK;
+  }
+  RG_CUDA(c, bufs.ensure(c->device, total, (int)clouds.size()));
+  std::vector<KnnCloud> desc(clouds.size());
+  int off = 0, chunk_off = 0;
+  for (size_t i = 0; i < clouds.size(); i++) {
+    desc[i].pts = clouds[i]->pts.p; desc[i].cov6 = clouds[i]->cov6.p; desc[i].knn_out = (knn_out && clouds.size() == 1) ? knn_out : nullptr;
+    desc[i].n = clouds[i]->n; desc[i].off = off; desc[i].chunk_off = chunk_off;
+    off += clouds[i]->n; chunk_off += (clouds[i]->n + 31) / 32;
+  }
+  KnnGroup g;
+  g.clouds = desc.data(); g.n_clouds = (int)desc.size(); g.total = (int)total; g.max_n = max_n; g.k = k; g.method = c->regularization_method;
+  g.s = bufs.view();
+  static const bool want_stats = std::getenv("ROLO_KNN_STATS") != nullptr;   // development aid: work counters of the chunk kernel on stderr
+  DevBuf<unsigned long long> stats;
+  if (want_stats) { RG_CUDA(c, stats.ensure(c->device, 8)); RG_CUDA(c, cudaMemsetAsync(stats.p, 0, 64, stream)); g.stats = stats.p; }
+  int own = 0;
+  RG_CUDA(c, launch_covariances_group(g, stream, &own));
+  g_launches += own;
+  if (want_stats) {
+    unsigned long long h[8]; int nf[2] = {0, 0};
+    cudaMemcpyAsync(h, stats.p, 64, cudaMemcpyDeviceToHost, stream); cudaMemcpyAsync(nf, bufs.fail.p, 8, cudaMemcpyDeviceToHost, stream); cudaStreamSynchronize(stream);
+    const double ch = (double)std::max<unsigned long long>(h[6], 1);
+    fprintf(stderr, "[knn stats] clouds %d points %zu chunks %llu | per chunk: raw %.1f staged %.1f events %.1f groups %.3f | pass/query %.1f | max raw %llu | fallback queries %d\n",
+            (int)clouds.size(), total, h[6], h[0] / ch, h[1] / ch, h[2] / ch, h[3] / ch, h[4] / (ch * 32.0), h[5], nf[0]);
+    stats.release();
+  }
+  for (Cloud* cl : clouds) cl->has_cov = true;
   return RG_OK;
+}
+
+int calc_cov(rg_ctx* c, Cloud& cl) {
+  if (use_device(c)) return RG_ERR_CUDA;
+  std::vector<Cloud*> one{&cl};
+  return calc_cov_group(c, one, c->knn, c->stream);
 }
 
 int check_grid(rg_ctx* c) {
@@ -201,8 +252,8 @@ int check_grid(rg_ctx* c) {
   return RG_OK;
 }
 
-int build_voxelmap(rg_ctx* c) {
-  if (use_device(c)) return RG_ERR_CUDA;
+// buffers + launch description of VmfVoxelMap::create_voxelmap over this context's target
+int prepare_voxel_build(rg_ctx* c, VoxelBuild& b) {
   if (int rc = check_grid(c)) return rc;
   if (c->tgt.n == 0) return set_err(c, RG_ERR_INVALID, "create_voxelmap: no target cloud");
   if (!c->tgt.has_cov) return set_err(c, RG_ERR_INVALID, "create_voxelmap: target covariances missing");
@@ -215,12 +266,18 @@ int build_voxelmap(rg_ctx* c) {
   RG_CUDA(c, c->sums.ensure(c->device, (size_t)n * 10));
   RG_CUDA(c, c->slot_of_point.ensure(c->device, n));
   RG_CUDA(c, c->counters.ensure(c->device, 2));
-  VoxelBuild b;
   b.pts = c->tgt.pts.p; b.cov6 = c->tgt.cov6.p; b.n = n; b.grid = make_grid(c);
   b.table = c->table.p; b.mask = c->mask; b.slot_of_point = c->slot_of_point.p; b.counters = c->counters.p;
   b.sums = c->sums.p; b.vox = c->vox.p;
+  return RG_OK;
+}
+
+int build_voxelmap(rg_ctx* c) {
+  if (use_device(c)) return RG_ERR_CUDA;
+  VoxelBuild b;
+  if (int rc = prepare_voxel_build(c, b)) return rc;
   RG_CUDA(c, launch_voxel_build(b, c->stream));
-  g_launches += 3;
+  g_launches += 4;
   c->voxel_ok = true; c->n_vox = -1; c->st_ok = false; c->have_corr = false;
   return RG_OK;
 }
@@ -404,9 +461,11 @@ int evaluate_single(rg_ctx* c, const host::Request& r, const double* g3, const d
 
 int ensure_covariances(rg_ctx* c) {
   // rot_vgicp_impl.hpp:153-158: recompute when the stored count differs from the cloud size
-  if (!c->src.has_cov) { if (int rc = calc_cov(c, c->src)) return rc; }
-  if (!c->tgt.has_cov) { if (int rc = calc_cov(c, c->tgt)) return rc; }
-  return RG_OK;
+  if (use_device(c)) return RG_ERR_CUDA;
+  std::vector<Cloud*> todo;
+  if (!c->src.has_cov) todo.push_back(&c->src);
+  if (!c->tgt.has_cov) todo.push_back(&c->tgt);
+  return calc_cov_group(c, todo, c->knn, c->stream);
 }
 
 int run_driver(rg_ctx* c, const double* g3, const double* l3, double dtn, double dtn1) {
@@ -475,7 +534,7 @@ void rg_destroy(rg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->src.release(); c->tgt.release();
   c->table.release(); c->vox.release(); c->sums.release(); c->slot_of_point.release(); c->counters.release();
-  c->codes_in.release(); c->codes_out.release(); c->idx_in.release(); c->idx_out.release(); c->bbox.release(); c->sorted.release(); c->cub_temp.release(); c->knn_idx.release(); c->bucket_start.release();
+  c->codes_in.release(); c->codes_out.release(); c->idx_in.release(); c->idx_out.release(); c->bbox.release(); c->sorted.release(); c->cub_temp.release(); c->knn_idx.release(); c->bucket_start.release(); c->knn.release();
   c->fe_raw.release(); c->fe_owner.release(); c->fe_row_count.release(); c->fe_col.release(); c->fe_start.release(); c->fe_end.release();
   c->fe_counts.release(); c->fe_picked.release(); c->fe_label.release(); c->fe_corner_cnt.release(); c->fe_surf_cnt.release();
   c->fe_range_image.release(); c->fe_prange.release(); c->fe_curv.release(); c->fe_full.release(); c->fe_extracted.release();
@@ -761,21 +820,44 @@ int rg_knn(rg_ctx* c, int which, int k, int32_t* out) {
   Cloud& cl = which == RG_SOURCE ? c->src : c->tgt;
   const int n = cl.n;
   if (n == 0 || k < 1 || k > 64 || n < k || !out) return set_err(c, RG_ERR_INVALID, "rg_knn: bad arguments");
-  RG_CUDA(c, c->codes_in.ensure(c->device, n)); RG_CUDA(c, c->codes_out.ensure(c->device, n));
-  RG_CUDA(c, c->idx_in.ensure(c->device, n)); RG_CUDA(c, c->idx_out.ensure(c->device, n));
-  RG_CUDA(c, c->sorted.ensure(c->device, n)); RG_CUDA(c, c->bbox.ensure(c->device, 8)); RG_CUDA(c, c->bucket_start.ensure(c->device, cov_bucket_table_entries()));
-  const size_t tb = cov_cub_temp_bytes(n);
-  RG_CUDA(c, c->cub_temp.ensure(c->device, tb));
+  // the product kernels (the same launch chain calculate_covariances runs) emit the neighbour SET of every point; the rows are
+  // put into the documented ascending (distance, index) order on the host, with the float distance of the reference's kd-tree
   DevBuf<int> dk;
   RG_CUDA(c, dk.ensure(c->device, (size_t)n * k));
-  CovLaunch L;
-  L.pts = cl.pts.p; L.n = n; L.k = k; L.method = c->regularization_method; L.cov6 = nullptr; L.knn = dk.p;
-  L.s.codes_in = c->codes_in.p; L.s.codes_out = c->codes_out.p; L.s.idx_in = c->idx_in.p; L.s.idx_out = c->idx_out.p;
-  L.s.sorted = c->sorted.p; L.s.cub_temp = c->cub_temp.p; L.s.cub_temp_bytes = tb; L.s.bbox = c->bbox.p; L.s.bucket_start = c->bucket_start.p;
-  RG_CUDA(c, launch_covariances(L, c->stream));
+  const int saved_k = c->k_correspondences;
+  const bool had_cov = cl.has_cov;
+  DevBuf<float> keep_cov;                      // rg_knn must not disturb installed covariances
+  RG_CUDA(c, keep_cov.ensure(c->device, (size_t)cl.n_pad * COV_PLANES));
+  RG_CUDA(c, cudaMemcpyAsync(keep_cov.p, cl.cov6.p, sizeof(float) * (size_t)cl.n_pad * COV_PLANES, cudaMemcpyDeviceToDevice, c->stream));
+  c->k_correspondences = k;
+  std::vector<Cloud*> one{&cl};
+  const int rc = calc_cov_group(c, one, c->knn, c->stream, dk.p);
+  c->k_correspondences = saved_k;
+  cudaMemcpyAsync(cl.cov6.p, keep_cov.p, sizeof(float) * (size_t)cl.n_pad * COV_PLANES, cudaMemcpyDeviceToDevice, c->stream);
+  cl.has_cov = had_cov;
+  if (rc) { cudaStreamSynchronize(c->stream); dk.release(); keep_cov.release(); return rc; }
+  std::vector<float4> hp((size_t)n);
   RG_CUDA(c, cudaMemcpyAsync(out, dk.p, sizeof(int) * (size_t)n * k, cudaMemcpyDeviceToHost, c->stream));
+  RG_CUDA(c, cudaMemcpyAsync(hp.data(), cl.pts.p, sizeof(float4) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
   RG_CUDA(c, cudaStreamSynchronize(c->stream));
-  dk.release();
+  dk.release(); keep_cov.release();
+  std::vector<std::pair<float, int>> row((size_t)k);
+  for (int i = 0; i < n; i++) {
+    int32_t* r = out + (size_t)i * k;
+    for (int t = 0; t < k; t++) {
+      const int id = r[t];
+      float d = std::numeric_limits<float>::infinity();
+      if (id >= 0 && id < n) {
+        volatile float dx = hp[i].x - hp[id].x, dy = hp[i].y - hp[id].y, dz = hp[i].z - hp[id].z;
+        volatile float xx = dx * dx, yy = dy * dy, zz = dz * dz;   // every product and sum rounded separately (no contraction)
+        volatile float s1 = xx + yy;
+        d = s1 + zz;
+      }
+      row[t] = {d, id};
+    }
+    std::sort(row.begin(), row.end());
+    for (int t = 0; t < k; t++) r[t] = row[t].second;
+  }
   return RG_OK;
 }
 
@@ -875,7 +957,7 @@ void rg_batch_destroy(rg_batch* b) {
   cudaSetDevice(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (size_t i = b->pairs.size(); i-- > 0;) rg_destroy(b->pairs[i]);   // pair 0 (stream owner) last
-  b->st_dev.release(); b->dyn_dev.release(); b->st_sub.release(); b->dyn_sub.release(); b->sched_dev.release();
+  b->st_dev.release(); b->dyn_dev.release(); b->st_sub.release(); b->dyn_sub.release(); b->sched_dev.release(); b->knn.release(); b->vox_builds.release();
   if (b->dyn_host) pool().pinned_free(b->dyn_host);
   if (b->result_host) pool().pinned_free(b->result_host);
   if (b->flag_host) pool().pinned_free(b->flag_host);
@@ -898,27 +980,47 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
   if (!b || !out_T) return set_err(nullptr, RG_ERR_INVALID, "rg_batch_align: bad arguments");
   const int P = (int)b->pairs.size();
   if (cudaSetDevice(b->device) != cudaSuccess) return set_err(nullptr, RG_ERR_CUDA, "cudaSetDevice failed");
-  // stage 1+2: covariances and voxel maps of every pair. Pairs are spread over a few setup streams so that the
-  // small, latency-bound kernels of one pair (radix-sort passes, bbox, Morton codes, voxel insert) overlap the
-  // big kNN kernels of the others; the batch stream joins them before the lock-step iterations start.
+  // stage 1: covariances of every cloud that lacks them, a GROUP of pairs per launch chain (one radix sort, one kNN + covariance
+  // launch for all clouds of the group). A group only waits for the uploads of its own pairs, so the H2D copies of later
+  // groups overlap the kernels of earlier ones.
   int noff = -1;
-  const int S = (int)b->setup_streams.size();
-  RG_CUDA(nullptr, cudaEventRecord(b->ev_inputs, b->stream));
-  for (int si = 0; si < S; si++) RG_CUDA(nullptr, cudaStreamWaitEvent(b->setup_streams[si], b->ev_inputs, 0));
-  int rc_setup = RG_OK;
-  for (int i = 0; i < P && rc_setup == RG_OK; i++) {
+  for (int i = 0; i < P; i++) {
     rg_ctx* c = b->pairs[i];
-    if (c->src.n == 0 || c->tgt.n == 0) { rc_setup = set_err(c, RG_ERR_INVALID, "batch align: source/target cloud not set"); break; }
+    if (c->src.n == 0 || c->tgt.n == 0) return set_err(c, RG_ERR_INVALID, "batch align: source/target cloud not set");
+    if (int rc = check_grid(c)) return rc;
     c->voxel_ok = false; c->st_ok = false; c->have_corr = false;
-    c->stream = b->setup_streams[i % S];
-    if ((rc_setup = check_grid(c)) == RG_OK && (rc_setup = ensure_covariances(c)) == RG_OK) rc_setup = build_voxelmap(c);
-    c->stream = b->stream;
   }
-  for (int si = 0; si < S; si++) {
-    cudaEventRecord(b->setup_events[si], b->setup_streams[si]);
-    cudaStreamWaitEvent(b->stream, b->setup_events[si], 0);
+  const int GROUP_PAIRS = 32;
+  for (int g0 = 0; g0 < P; g0 += GROUP_PAIRS) {
+    const int g1 = std::min(P, g0 + GROUP_PAIRS);
+    std::vector<char> done(g1 - g0, 0);
+    for (int i = g0; i < g1; i++) {
+      rg_ctx* c = b->pairs[i];
+      if (c->side_pending && c->upload_stream && c->upload_stream != b->stream) { RG_CUDA(c, cudaStreamWaitEvent(b->stream, c->ev_upload, 0)); c->side_pending = false; }
+    }
+    for (int i = g0; i < g1; i++) {
+      if (done[i - g0]) continue;
+      rg_ctx* lead = b->pairs[i];
+      std::vector<Cloud*> todo;
+      for (int j = i; j < g1; j++) {   // pairs of this group with the same (k, regulariser) share a launch chain
+        rg_ctx* c = b->pairs[j];
+        if (done[j - g0] || c->k_correspondences != lead->k_correspondences || c->regularization_method != lead->regularization_method) continue;
+        done[j - g0] = 1;
+        if (!c->tgt.has_cov) todo.push_back(&c->tgt);
+        if (!c->src.has_cov) todo.push_back(&c->src);
+      }
+      if (int rc = calc_cov_group(lead, todo, b->knn, b->stream)) return rc;
+    }
   }
-  if (rc_setup != RG_OK) return rc_setup;
+  // stage 2: every voxel map by one launch chain
+  {
+    std::vector<VoxelBuild> builds(P);
+    for (int i = 0; i < P; i++) if (int rc = prepare_voxel_build(b->pairs[i], builds[i])) return rc;
+    RG_CUDA(nullptr, b->vox_builds.ensure(b->device, P));
+    RG_CUDA(nullptr, launch_voxel_build_batch(builds.data(), b->vox_builds.p, P, b->stream));
+    g_launches += 4;
+    for (int i = 0; i < P; i++) { rg_ctx* c = b->pairs[i]; c->voxel_ok = true; c->n_vox = -1; c->st_ok = false; c->have_corr = false; }
+  }
   for (int i = 0; i < P; i++) {
     rg_ctx* c = b->pairs[i];
     if (int rc = prepare_linearize(c)) return rc;

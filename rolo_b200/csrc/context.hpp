@@ -106,6 +106,10 @@ struct DevBuf {
   T* p = nullptr; size_t cap = 0; int device = 0;
   cudaError_t ensure(int dev, size_t count) {
     if (count <= cap && p) return cudaSuccess;
+    // growth: the old block goes back to the process-global pool, where any stream of any context may pick it up at once.
+    // Kernels queued on it may still be running, so the device is drained first (growth is rare: buffers keep their size class
+    // from frame to frame).
+    if (p) { cudaSetDevice(device); cudaDeviceSynchronize(); }
     release();
     device = dev;
     void* q = nullptr;
@@ -115,6 +119,40 @@ struct DevBuf {
     return cudaSuccess;
   }
   void release() { if (p) pool().dev_free(p); p = nullptr; cap = 0; }
+};
+
+// scratch of one covariance-estimation group (covariance.cuh: KnnScratch), sized for `total` points in `n_clouds` clouds
+struct KnnBufs {
+  DevBuf<unsigned long long> codes_a, codes_b;
+  DevBuf<int> idx_a, idx_b, bbox, bucket, fail;
+  DevBuf<float4> sorted;
+  DevBuf<unsigned char> cub_temp;
+  DevBuf<KnnCloud> clouds;
+  size_t cub_bytes = 0;
+  cudaError_t ensure(int dev, size_t total, int n_clouds) {
+    cudaError_t e;
+    if ((e = codes_a.ensure(dev, total)) != cudaSuccess) return e;
+    if ((e = codes_b.ensure(dev, total)) != cudaSuccess) return e;
+    if ((e = idx_a.ensure(dev, total)) != cudaSuccess) return e;
+    if ((e = idx_b.ensure(dev, total)) != cudaSuccess) return e;
+    if ((e = sorted.ensure(dev, total)) != cudaSuccess) return e;
+    if ((e = bbox.ensure(dev, (size_t)n_clouds * 8)) != cudaSuccess) return e;
+    if ((e = bucket.ensure(dev, (size_t)n_clouds * cov_bucket_table_entries())) != cudaSuccess) return e;
+    if ((e = fail.ensure(dev, 2 + 2 * total)) != cudaSuccess) return e;
+    if ((e = clouds.ensure(dev, n_clouds)) != cudaSuccess) return e;
+    cub_bytes = cov_cub_temp_bytes((int)total, n_clouds);
+    return cub_temp.ensure(dev, cub_bytes);
+  }
+  KnnScratch view() const {
+    KnnScratch s;
+    s.codes_a = codes_a.p; s.codes_b = codes_b.p; s.idx_a = idx_a.p; s.idx_b = idx_b.p; s.sorted = sorted.p;
+    s.cub_temp = cub_temp.p; s.cub_temp_bytes = cub_bytes; s.bbox = bbox.p; s.bucket_start = bucket.p; s.fail = fail.p; s.clouds = clouds.p;
+    return s;
+  }
+  void release() {
+    codes_a.release(); codes_b.release(); idx_a.release(); idx_b.release(); bbox.release(); bucket.release(); fail.release();
+    sorted.release(); cub_temp.release(); clouds.release();
+  }
 };
 
 struct Cloud {
@@ -168,6 +206,7 @@ struct rg_ctx {
   DevBuf<float4> sorted;
   DevBuf<unsigned char> cub_temp;
   DevBuf<int> knn_idx, bucket_start;
+  KnnBufs knn;                          // group scratch of calculate_covariances (stand-alone contexts; a batch owns its own)
 
   // linearize
   DevBuf<int> corr; int corr_noff = 0;
@@ -244,6 +283,8 @@ struct rg_batch {
   std::vector<int> active;
   DevBuf<LinStatic> st_sub; DevBuf<LinDyn> dyn_sub;
   DevBuf<int> sched_dev; std::vector<int> sched_group; int sched_grid = 0, sched_tiles = 0;   // schedule of the last launched group
+  KnnBufs knn;                          // covariance estimation of many clouds per launch chain
+  DevBuf<VoxelBuild> vox_builds;        // voxel-map build descriptors of all pairs
   std::vector<cudaStream_t> setup_streams;   // covariance / voxel-map stages of different pairs overlap on these
   std::vector<cudaEvent_t> setup_events;
   cudaEvent_t ev_inputs = nullptr;

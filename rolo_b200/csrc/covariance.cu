@@ -1,25 +1,35 @@
-// covariance.cu — RotVGICP::calculate_covariances on the GPU (rot_vgicp_impl.hpp:421-496).
+// covariance.cu — RotVGICP::calculate_covariances on the GPU (rot_vgicp_impl.hpp:421-496) and the Morton-ordered spatial index.
 //
 // Reference: per point, pcl::search::KdTree::nearestKSearch(k=20) (FLANN, float L2), mean-centre the
 // 4 x k neighbour matrix, cov = N N^T / k, regularise through JacobiSVD (PLANE: U diag(1,1,1e-3) V^T).
-// Here (exact, no approximation of the neighbour set):
-//   1. bounding box, 39-bit Morton codes (13 bits/axis: 5 radix passes), radix sort of (code, index)  [cub::DeviceRadixSort
-//      is the only library call: plumbing, not the hot op]
-//   2. one thread per query walks an implicit octree over the sorted codes: at level L the 3x3x3 block
-//      of level-L cells around the query is scanned (each cell = one contiguous range found by binary
-//      search); the result is exact once the k-th distance is below the distance to the block
-//      boundary, otherwise the level is coarsened. The start level comes from the common prefix of
-//      the query's Morton neighbours, so dense (near) and sparse (far) regions both scan O(100) points.
-//   3. neighbours ordered by (float distance, index) exactly like the oracle; covariance in fp64;
-//      symmetric 3x3 eigen-decomposition by cyclic Jacobi (fp64) gives the SVD of the PSD matrix.
-// Float distances are accumulated x,y,z without FMA contraction so the neighbour sets match the
-// CPU oracle bit for bit.
+// Here (exact, no approximation of the neighbour set), for a whole GROUP of clouds per launch chain:
+//   1. per cloud bounding box, 39-bit Morton codes (13 bits/axis), ONE radix sort of (cloud id | code, index) over the
+//      concatenated group [cub::DeviceRadixSort is the only library call: plumbing, not the hot op], Morton-ordered copy of the
+//      points, bucket table over the top code bits.
+//   2. knn_chunk_kernel: one WARP owns 32 Morton-consecutive queries (one per lane) and searches them TOGETHER:
+//        a. each lane bounds its k-th neighbour distance by the k Morton-order neighbours on its left, around it and on its right
+//           (3 windows, the smallest maximum): tau0;
+//        b. the union of the 32 balls (q, sqrt(tau0)) gives one box; the box is covered by <= 32 octree cells of one level,
+//           each cell is one contiguous range of the sorted array (one bucketed binary-search pair per LANE, not per query);
+//        c. the candidates of those ranges are clipped against the box and staged in shared memory once; every lane scans
+//           all of them (broadcast reads), keeping the k smallest DISTANCES in registers as a sorted min/max chain
+//           (2 FMNMX per slot, no index payload, no divergence) and appending the position of every candidate that was at
+//           most the running k-th distance to a per-lane pass list in shared memory;
+//        d. tau* = the exact k-th smallest distance. The neighbour SET is {d < tau*} plus the (k - m) smallest original
+//           indices among {d == tau*}, taken from the pass list: the same set the oracle's (distance, index) order selects;
+//        e. epilogue in the same kernel: mean / scatter in fp64, cyclic-Jacobi eigen-decomposition, regulariser, tile-planar
+//           fp32 store. The neighbour lists (21 MB per 262144-point cloud) are never written.
+//      Anything unusual (pass-list or tie overflow, non-finite query) puts the query on a fail list;
+//   3. knn_fallback_kernel serves that list with the warp-per-query octree search (sorted top-32 across the lanes) + the same
+//      epilogue. It is the slow exact path, normally empty.
+// Float distances are accumulated x,y,z without FMA contraction so the neighbour sets match the CPU oracle bit for bit.
 
 #include "covariance.cuh"
 #include "morton.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <float.h>
+#include <algorithm>
 #include <math_constants.h>
 #include <limits.h>
 
@@ -27,14 +37,26 @@ namespace rolo {
 
 namespace {
 
-__global__ void bbox_init_kernel(int* bbox) {
-  if (threadIdx.x < 3) bbox[threadIdx.x] = INT_MAX;
-  else if (threadIdx.x < 6) bbox[threadIdx.x] = INT_MIN;
+// a cloud descriptor reaches the index kernels either from a device array (group path, one per blockIdx.y) or by value
+struct CloudRef {
+  const KnnCloud* arr;
+  KnnCloud one;
+};
+__device__ __forceinline__ KnnCloud get_cloud(const CloudRef& r) { return r.arr ? r.arr[blockIdx.y] : r.one; }
+
+__global__ void bbox_init_kernel(int* bbox, int n_clouds) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_clouds * 8) return;
+  const int d = t & 7;
+  bbox[t] = d < 3 ? INT_MAX : (d < 6 ? INT_MIN : 0);
 }
 
-__global__ void bbox_kernel(const float4* __restrict__ pts, int n, int* bbox) {
+__global__ void bbox_kernel(CloudRef ref, int* bbox_all) {
+  const KnnCloud C = get_cloud(ref);
+  int* bbox = bbox_all + blockIdx.y * 8;
+  const float4* __restrict__ pts = C.pts;
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C.n; i += gridDim.x * blockDim.x) {
     const float4 p = pts[i];
     mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
     mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
@@ -63,33 +85,40 @@ __global__ void bbox_kernel(const float4* __restrict__ pts, int n, int* bbox) {
   }
 }
 
-__global__ void morton_kernel(const float4* __restrict__ pts, int n, const int* __restrict__ bbox,
-                              unsigned long long* __restrict__ codes, int* __restrict__ idx) {
+// key = cloud id << 39 | Morton code: one radix sort orders every cloud of the group
+__global__ void morton_kernel(CloudRef ref, const int* __restrict__ bbox_all, unsigned long long* __restrict__ codes, int* __restrict__ idx) {
+  const KnnCloud C = get_cloud(ref);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const Quant q = make_quant(bbox);
-  const float4 p = pts[i];
+  if (i >= C.n) return;
+  const Quant q = make_quant(bbox_all + blockIdx.y * 8);
+  const float4 p = C.pts[i];
   unsigned ix, iy, iz;
   quantize(q, p.x, p.y, p.z, ix, iy, iz);
-  codes[i] = morton3(ix, iy, iz);
-  idx[i] = i;
+  codes[C.off + i] = ((unsigned long long)blockIdx.y << CODE_BITS) | morton3(ix, iy, iz);
+  idx[C.off + i] = i;
 }
 
-// Morton-ordered copy of the points (w = original index) + the packed cell coordinates (ix | iy << 21 | iz << 42) of each
-// sorted point: the kNN kernel needs them per query, and de-interleaving the code there would cost ~100 warp-instructions
-// per query instead of ~100 per 32 points here. `cells` reuses the unsorted-code buffer, which is dead after the sort.
-__global__ void gather_sorted_kernel(const float4* __restrict__ pts, const int* __restrict__ idx, int n, const int* __restrict__ bbox,
-                                     float4* __restrict__ sorted, unsigned long long* __restrict__ cells) {
+// Morton-ordered copy of the points (w = original index) + the sorted codes with the cloud bits stripped
+__global__ void gather_sorted_kernel(CloudRef ref, const int* __restrict__ idx_sorted, const unsigned long long* __restrict__ codes_sorted,
+                                     float4* __restrict__ sorted, unsigned long long* __restrict__ codes_clean) {
+  const KnnCloud C = get_cloud(ref);
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  const int i = idx[j];
-  float4 p = pts[i];
-  const Quant q = make_quant(bbox);
-  unsigned ix, iy, iz;
-  quantize(q, p.x, p.y, p.z, ix, iy, iz);          // identical to morton_kernel's
-  cells[j] = (unsigned long long)ix | ((unsigned long long)iy << 21) | ((unsigned long long)iz << 42);
+  if (j >= C.n) return;
+  const int i = idx_sorted[C.off + j];
+  float4 p = C.pts[i];
   p.w = __int_as_float(i);
-  sorted[j] = p;
+  sorted[C.off + j] = p;
+  if (codes_clean) codes_clean[C.off + j] = codes_sorted[C.off + j] & ((1ull << CODE_BITS) - 1ull);
+}
+
+// bucket_start[b] = first sorted position whose code has top bits >= b (b = 0 .. N_BUCKETS): every later
+// lower_bound only searches inside one bucket
+__global__ void bucket_table_kernel(CloudRef ref, const unsigned long long* __restrict__ codes_clean, int* __restrict__ bucket_all) {
+  const KnnCloud C = get_cloud(ref);
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b > N_BUCKETS) return;
+  int* bucket_start = bucket_all + (size_t)blockIdx.y * (N_BUCKETS + 1);
+  bucket_start[b] = (b == N_BUCKETS) ? C.n : lower_bound_u64(codes_clean + C.off, C.n, (unsigned long long)b << BUCKET_SHIFT);
 }
 
 __device__ __forceinline__ bool cand_less(float da, int ia, float db, int ib) { return da < db || (da == db && ia < ib); }
@@ -197,163 +226,516 @@ __device__ void regularize(const double cov[6], int method, double out[6]) {
 }
 
 
-// ---------------------------------------------------------------------------------------------------
-// exact kNN, one WARP per query (k <= 32).
-//  * lanes 0..26 each locate one cell of the 3x3x3 block (two binary searches in parallel instead of 54
-//    in sequence); a warp scan of the cell counts gives the candidate total, which also steers the level:
-//    too many candidates -> finer level, fewer than k -> coarser, before anything is scanned;
-//  * candidates are scanned 32 at a time (coalesced), the current top-32 lives one element per lane, sorted
-//    by (distance, index); a batch in which nobody beats the k-th distance costs one ballot; otherwise the
-//    winners are inserted by shuffle (few) or the batch is bitonic-sorted and merged (many).
-// ---------------------------------------------------------------------------------------------------
-constexpr int KNN_QPW = 4;            // queries handled sequentially by one warp
-constexpr int KNN_CAND_CAP = 1024;    // prefer a finer level when the block holds more candidates than this
-// bucket_start[b] = first sorted position whose code has top bits >= b (b = 0 .. N_BUCKETS): every later
-// lower_bound only searches inside one bucket
-__global__ void bucket_table_kernel(const unsigned long long* __restrict__ codes, int n, int* __restrict__ bucket_start) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b > N_BUCKETS) return;
-  bucket_start[b] = (b == N_BUCKETS) ? n : lower_bound_u64(codes, n, (unsigned long long)b << BUCKET_SHIFT);
+
+__device__ __forceinline__ float dist2_exact(const float4& q, const float4& p) {
+  const float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-__global__ void __launch_bounds__(256, 5)        // 48 registers: 40 warps/SM measured 4 % faster than 32
-knn_warp_kernel(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes, const unsigned long long* __restrict__ cells,
-                const int* __restrict__ bucket_start, int n, int k, const int* __restrict__ bbox, int* __restrict__ knn_out) {
+__device__ __forceinline__ void store_cov6(float* __restrict__ cov6, int i, const double out[6]) {
+  const size_t base = (size_t)(i / TILE_PTS) * COV_PLANES * TILE_PTS + (i % TILE_PTS);
+  #pragma unroll
+  for (int t = 0; t < 6; t++) cov6[base + (size_t)t * TILE_PTS] = (float)out[t];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// chunk-cooperative exact kNN + covariance (see the file header). KC = compile-time capacity of the distance chain (k <= KC).
+// ---------------------------------------------------------------------------------------------------
+constexpr int KNN_WARPS = 8;          // warps (= chunks of 32 queries) per CTA; warps are independent (no CTA barrier)
+constexpr int KNN_STAGE = 128;        // staged candidates per warp (float4)
+constexpr int KNN_PL = 64;            // pass-list entries per lane
+constexpr int KNN_PEND = 8;           // distances waiting for the chain, per lane
+constexpr int KNN_TIE = 16;           // tie entries per lane (aliases the stage buffer: 128 float4 = 16 x 32 ints)
+constexpr int KNN_RAW_CAP = 3072;      // candidates of one group before clipping; above it the widest lanes go to the fallback kernel
+constexpr int KNN_WINDOW = 64;        // Morton-order neighbours scanned first (the chunk itself + 16 before + 16 after)
+constexpr size_t KNN_SMEM_WARP = KNN_STAGE * sizeof(float4) + (size_t)KNN_PL * 32 * sizeof(int) + (size_t)KNN_PEND * 32 * sizeof(float);
+constexpr size_t KNN_SMEM = (size_t)KNN_WARPS * KNN_SMEM_WARP;
+static_assert(KNN_TIE * 32 * sizeof(int) <= KNN_STAGE * sizeof(float4), "tie buffer aliases the stage buffer");
+static_assert(KNN_WINDOW <= KNN_STAGE, "the window is staged as one tile");
+
+template <int KC>
+__device__ __forceinline__ void chain_insert(float (&a)[KC], float v) {
+  // a is ascending; afterwards it holds the KC smallest of (a, v): slot i becomes min(a[i], max(a[i-1], v))
+  #pragma unroll
+  for (int i = KC - 1; i >= 1; i--) a[i] = fminf(a[i], fmaxf(a[i - 1], v));
+  a[0] = fminf(a[0], v);
+}
+
+// per-lane search state of the chunk kernel
+template <int KC>
+struct KnnLane {
+  float a[KC];                // ascending; a[KC-1] = k-th smallest distance seen (the low KC-k slots are pinned at -1)
+  int npass, npend;
+  bool overflow;
+};
+
+// chain update with every pending distance (all lanes in lock step), then, if a pass list is nearly full, drop its entries that
+// fell behind the running k-th distance
+template <int KC>
+__device__ __forceinline__ void knn_flush(KnnLane<KC>& L, const float4 q, const float4* __restrict__ sorted, int* plist, const float* pend) {
+  const unsigned FULL = 0xffffffffu;
+  const int mx = __reduce_max_sync(FULL, L.npend);
+  #pragma unroll 1
+  for (int e = 0; e < mx; e++) chain_insert<KC>(L.a, e < L.npend ? pend[e * 32] : CUDART_INF_F);
+  L.npend = 0;
+  if (__any_sync(FULL, L.npass > KNN_PL - 2 * KNN_PEND)) {
+    const float cur = L.a[KC - 1];
+    const int have = min(L.npass, KNN_PL);
+    int m2 = 0;
+    #pragma unroll 1
+    for (int e = 0; e < have; e++) {
+      const int pos = plist[e * 32];
+      if (dist2_exact(q, __ldg(sorted + pos)) <= cur) { plist[m2 * 32] = pos; m2++; }
+    }
+    if (L.npass > KNN_PL) L.overflow = true;               // entries were dropped before this prune
+    L.npass = m2;
+    if (L.npass > KNN_PL - 2 * KNN_PEND) L.overflow = true;   // that many candidates inside the k-th distance: exact ties en masse
+  }
+}
+
+// every lane of the group scans the `ns` staged candidates (ns even; a padding entry has NaN coordinates)
+template <int KC>
+__device__ __forceinline__ void knn_scan_tile(KnnLane<KC>& L, const bool act, const float4 q, const float4* __restrict__ stage, int ns,
+                                              const float4* __restrict__ sorted, int* plist, float* pend, unsigned& st_events) {
+  const unsigned FULL = 0xffffffffu;
+  #pragma unroll 1
+  for (int s = 0; s < ns; s += 2) {
+    const float4 p0 = stage[s], p1 = stage[s + 1];          // broadcast reads
+    const float d0 = dist2_exact(q, p0), d1 = dist2_exact(q, p1);
+    const float thr = L.a[KC - 1];
+    const bool pass0 = act && d0 <= thr, pass1 = act && d1 <= thr;
+    if (__any_sync(FULL, pass0 || pass1)) {
+      st_events++;
+      if (pass0) { if (L.npass < KNN_PL) plist[L.npass * 32] = __float_as_int(p0.w); L.npass++; pend[L.npend * 32] = d0; L.npend++; }
+      if (pass1) { if (L.npass < KNN_PL) plist[L.npass * 32] = __float_as_int(p1.w); L.npass++; pend[L.npend * 32] = d1; L.npend++; }
+      if (__any_sync(FULL, L.npend >= KNN_PEND - 1)) knn_flush<KC>(L, q, sorted, plist, pend);
+    }
+  }
+  knn_flush<KC>(L, q, sorted, plist, pend);
+}
+
+template <int KC>
+__global__ void __launch_bounds__(KNN_WARPS * 32, 2)
+knn_chunk_kernel(const KnnCloud* __restrict__ clouds, int n_clouds, int total_chunks, const float4* __restrict__ sorted_all,
+                 const unsigned long long* __restrict__ codes_all, const int* __restrict__ bucket_all, const int* __restrict__ bbox_all,
+                 int* __restrict__ fail, int k, int method, unsigned long long* stats) {
+  extern __shared__ __align__(16) unsigned char knn_smem[];
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* wsm = knn_smem + (size_t)warp * KNN_SMEM_WARP;
+  float4* stage = reinterpret_cast<float4*>(wsm);
+  int* plist = reinterpret_cast<int*>(wsm + KNN_STAGE * sizeof(float4)) + lane;                                         // [slot * 32]
+  float* pend = reinterpret_cast<float*>(wsm + KNN_STAGE * sizeof(float4) + (size_t)KNN_PL * 32 * sizeof(int)) + lane;  // [slot * 32]
+  int* tie = reinterpret_cast<int*>(stage) + lane;                                                                      // [slot * 32]
+
+  // persistent warps: the work per chunk varies by orders of magnitude (sparse far returns, chunks that straddle a jump of the
+  // Morton curve), so every warp draws its next chunk from a global ticket instead of owning a fixed one
+  #pragma unroll 1
+  for (;;) {
+  int chunk = 0;
+  if (lane == 0) chunk = atomicAdd(fail + 1, 1);
+  chunk = __shfl_sync(FULL, chunk, 0);
+  if (chunk >= total_chunks) break;
+  int cloud;
+  {
+    int lo_c = 0, hi_c = n_clouds - 1;                      // last cloud whose first chunk is <= chunk
+    while (lo_c < hi_c) { const int mid = (lo_c + hi_c + 1) >> 1; if (__ldg(&clouds[mid].chunk_off) <= chunk) lo_c = mid; else hi_c = mid - 1; }
+    cloud = lo_c;
+  }
+  const KnnCloud C = clouds[cloud];
+  const int n = C.n;
+  const int j0 = (chunk - C.chunk_off) * 32;
+  const float4* __restrict__ sorted = sorted_all + C.off;
+  const unsigned long long* __restrict__ codes = codes_all + C.off;
+  const int* __restrict__ bucket_start = bucket_all + (size_t)cloud * (N_BUCKETS + 1);
+
+  const int j = j0 + lane;
+  const bool in_cloud = j < n;
+  const float4 q = __ldg(sorted + min(j, n - 1));            // lanes past the end repeat the last point and write nothing
+  bool finite = (q.x - q.x == 0.f) && (q.y - q.y == 0.f) && (q.z - q.z == 0.f);
+  bool kicked = false;                                       // handed to the fallback kernel (warp-per-query search)
+
+  KnnLane<KC> L;
+  #pragma unroll
+  for (int i = 0; i < KC; i++) L.a[i] = (i < KC - k) ? -1.0f : CUDART_INF_F;   // the low KC-k slots are pinned below every distance
+  L.npass = 0; L.npend = 0; L.overflow = false;
+  unsigned st_staged = 0, st_events = 0, st_groups = 0, st_raw = 0;
+
+  // ---- a. the Morton-order neighbourhood of the chunk first: 64 candidates that bound every lane's k-th distance tightly
+  const int wcnt = min(KNN_WINDOW, n);
+  const int wlo = max(0, min(j0 - 16, n - wcnt));
+  {
+    #pragma unroll
+    for (int h = 0; h < KNN_WINDOW / 32; h++) {
+      const int w = h * 32 + lane;
+      float4 c = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, 0.f);
+      if (w < wcnt) { c = __ldg(sorted + wlo + w); c.w = __int_as_float(wlo + w); }
+      stage[w] = c;
+    }
+    __syncwarp();
+    knn_scan_tile<KC>(L, finite, q, stage, KNN_WINDOW, sorted, plist, pend, st_events);
+    __syncwarp();
+  }
+
+  // ---- b. search box of every lane (rounded outwards); consecutive lanes whose boxes are disjoint share no candidate, so the
+  //         chunk is cut there and the groups are searched one after the other (a chunk that straddles a jump of the Morton curve
+  //         would otherwise drag in everything between its two ends)
+  float l0, l1, l2, h0, h1, h2;
+  {
+    const float R = __fmul_ru(__fsqrt_ru(L.a[KC - 1]), 1.000001f);
+    l0 = __fsub_rd(q.x, R); l1 = __fsub_rd(q.y, R); l2 = __fsub_rd(q.z, R);
+    h0 = __fadd_ru(q.x, R); h1 = __fadd_ru(q.y, R); h2 = __fadd_ru(q.z, R);
+  }
+  unsigned cuts;
+  {
+    const float nl0 = __shfl_down_sync(FULL, l0, 1), nl1 = __shfl_down_sync(FULL, l1, 1), nl2 = __shfl_down_sync(FULL, l2, 1);
+    const float nh0 = __shfl_down_sync(FULL, h0, 1), nh1 = __shfl_down_sync(FULL, h1, 1), nh2 = __shfl_down_sync(FULL, h2, 1);
+    const bool nfin = __shfl_down_sync(FULL, finite ? 1 : 0, 1) != 0;
+    const bool overlap = nl0 <= h0 && l0 <= nh0 && nl1 <= h1 && l1 <= nh1 && nl2 <= h2 && l2 <= nh2;   // false for NaN boxes
+    cuts = __ballot_sync(FULL, lane < 31 && !(overlap && finite && nfin)) | 0x80000000u;
+  }
+  const Quant qn = make_quant(bbox_all + cloud * 8);
+  #pragma unroll 1
+  for (int gstart = 0; gstart < 32;) {
+    const int gend = gstart + __ffs(cuts >> gstart) - 1;    // the group is lanes gstart..gend
+    const bool act = finite && lane >= gstart && lane <= gend;
+    gstart = gend + 1;
+    if (!__any_sync(FULL, act)) continue;
+    st_groups++;
+    const float INF = CUDART_INF_F;
+    float lox, loy, loz, hix, hiy, hiz;
+    int lo, cnt, incl, total, excl;
+    bool act_g = act;
+    #pragma unroll 1
+    for (int attempt = 0;; attempt++) {
+      lox = ordered_to_float(__reduce_min_sync(FULL, float_to_ordered(act_g ? l0 : INF)));
+      loy = ordered_to_float(__reduce_min_sync(FULL, float_to_ordered(act_g ? l1 : INF)));
+      loz = ordered_to_float(__reduce_min_sync(FULL, float_to_ordered(act_g ? l2 : INF)));
+      hix = ordered_to_float(__reduce_max_sync(FULL, float_to_ordered(act_g ? h0 : -INF)));
+      hiy = ordered_to_float(__reduce_max_sync(FULL, float_to_ordered(act_g ? h1 : -INF)));
+      hiz = ordered_to_float(__reduce_max_sync(FULL, float_to_ordered(act_g ? h2 : -INF)));
+      // covering cells: the finest level at which the box spans <= 32 cells; lane c looks up cell c (one range of the sorted array)
+      lo = 0; cnt = 0;
+      {
+        unsigned ix0, iy0, iz0, ix1, iy1, iz1;
+        quantize(qn, lox, loy, loz, ix0, iy0, iz0);
+        quantize(qn, hix, hiy, hiz, ix1, iy1, iz1);
+        const unsigned ext = max(max(ix1 - ix0, iy1 - iy0), iz1 - iz0);
+        int sh = max(0, 30 - __clz((int)ext));              // ext >> sh < 4
+        int ncx, ncy, ncz;
+        #pragma unroll 1
+        for (;; sh++) {
+          ncx = (int)(ix1 >> sh) - (int)(ix0 >> sh) + 1; ncy = (int)(iy1 >> sh) - (int)(iy0 >> sh) + 1; ncz = (int)(iz1 >> sh) - (int)(iz0 >> sh) + 1;
+          if (ncx * ncy * ncz <= 32 || sh >= MORTON_BITS) break;
+        }
+        if (lane < ncx * ncy * ncz) {
+          const unsigned cx = (ix0 >> sh) + (unsigned)(lane % ncx), cy = (iy0 >> sh) + (unsigned)((lane / ncx) % ncy), cz = (iz0 >> sh) + (unsigned)(lane / (ncx * ncy));
+          const unsigned long long pre = morton3(cx, cy, cz);
+          lo = lower_bound_bucketed(codes, bucket_start, pre << (3 * sh));
+          const int hi = (sh >= MORTON_BITS) ? n : lower_bound_bucketed(codes, bucket_start, (pre + 1ull) << (3 * sh));
+          cnt = hi - lo;
+        }
+      }
+      incl = cnt;
+      #pragma unroll
+      for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
+      total = __shfl_sync(FULL, incl, 31);
+      excl = incl - cnt;
+      if (total <= KNN_RAW_CAP) break;
+      // too many candidates for a lock-step scan: the lane with the widest box goes to the fallback kernel, which searches one
+      // query with all 32 lanes; after a few of those the whole group goes
+      const float myR = act_g ? (h0 - l0) : -1.0f;
+      const float maxR = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fmaxf(myR, 0.f))));
+      const bool all_go = attempt >= 3;
+      if (act_g && (all_go || myR == maxR)) { kicked = true; act_g = false; }
+      if (!__any_sync(FULL, act_g)) { total = 0; break; }
+    }
+    st_raw += total;
+    const bool act2 = act_g;
+
+    // ---- c. stage the candidates of the ranges (clipped against the box, the window left out) and scan them tile by tile
+    int ns = 0;
+    #pragma unroll 1
+    for (int base = 0; base < total; base += 32) {
+      const int g = base + lane;
+      int o = 0, b = 31;                                     // owning cell: the first lane whose inclusive count exceeds g
+      #pragma unroll
+      for (int s = 0; s < 5; s++) {
+        const int mid = (o + b) >> 1;
+        const int v = __shfl_sync(FULL, incl, mid);
+        if (v <= g) o = mid + 1; else b = mid;
+      }
+      const int cell_lo = __shfl_sync(FULL, lo, o), cell_ex = __shfl_sync(FULL, excl, o);
+      bool keep = false;
+      float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (g < total) {
+        const int pos = cell_lo + (g - cell_ex);
+        c = __ldg(sorted + pos);
+        keep = c.x >= lox && c.x <= hix && c.y >= loy && c.y <= hiy && c.z >= loz && c.z <= hiz && (unsigned)(pos - wlo) >= (unsigned)wcnt;
+        c.w = __int_as_float(pos);
+      }
+      const unsigned km = __ballot_sync(FULL, keep);
+      if (keep) stage[ns + __popc(km & ((1u << lane) - 1u))] = c;
+      ns += __popc(km);
+      if (ns > KNN_STAGE - 32 || base + 32 >= total) {
+        if ((ns & 1) && lane == 0) stage[ns] = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, 0.f);
+        __syncwarp();
+        st_staged += ns;
+        knn_scan_tile<KC>(L, act2, q, stage, (ns + 1) & ~1, sorted, plist, pend, st_events);
+        ns = 0;
+        __syncwarp();
+      }
+    }
+  }
+  if (stats) {
+    if (lane == 0) {
+      atomicAdd(stats + 0, (unsigned long long)st_raw); atomicAdd(stats + 1, (unsigned long long)st_staged); atomicAdd(stats + 2, (unsigned long long)st_events);
+      atomicAdd(stats + 3, (unsigned long long)st_groups); atomicAdd(stats + 6, 1ull); atomicMax(stats + 5, (unsigned long long)st_raw);
+    }
+    atomicAdd(stats + 4, (unsigned long long)L.npass);
+  }
+
+  // ---- d. the neighbour set: everything below tau*, then the smallest original indices among the ties at tau*
+  const float tau = L.a[KC - 1];
+  const int npass = min(L.npass, KNN_PL);
+  int m = 0, nt = 0;
+  #pragma unroll 1
+  for (int e = 0; e < npass; e++) {
+    const int pos = plist[e * 32];
+    const float d = dist2_exact(q, __ldg(sorted + pos));
+    if (d < tau) { plist[m * 32] = pos; m++; }
+    else if (d == tau) { if (nt < KNN_TIE) tie[nt * 32] = pos; nt++; }
+  }
+  const int need = k - m;
+  bool ok = finite && !kicked && !L.overflow && L.npass <= KNN_PL && need >= 1 && nt >= need && nt <= KNN_TIE;
+  if (ok) {
+    if (nt == need) {
+      for (int u = 0; u < nt; u++) plist[(m + u) * 32] = tie[u * 32];
+    } else {
+      int prev = -1;
+      for (int u = 0; u < need; u++) {
+        int best = INT_MAX, best_pos = 0;
+        for (int v = 0; v < nt; v++) {
+          const int pos = tie[v * 32];
+          const int oi = __float_as_int(__ldg(sorted + pos).w);
+          if (oi > prev && oi < best) { best = oi; best_pos = pos; }
+        }
+        plist[(m + u) * 32] = best_pos; prev = best;
+      }
+    }
+  }
+
+  // ---- e. covariance of the k neighbours (rot_vgicp_impl.hpp:446-456) + regulariser (:458-492)
+  if (in_cloud) {
+    const int self = __float_as_int(q.w);
+    if (ok) {
+      double sx = 0, sy = 0, sz = 0;
+      #pragma unroll 1
+      for (int u = 0; u < k; u++) { const float4 p = __ldg(sorted + plist[u * 32]); sx += (double)p.x; sy += (double)p.y; sz += (double)p.z; }
+      const double mx = sx / k, my = sy / k, mz = sz / k;
+      double cc[6] = {0, 0, 0, 0, 0, 0};
+      #pragma unroll 1
+      for (int u = 0; u < k; u++) {
+        const float4 p = __ldg(sorted + plist[u * 32]);
+        const double dx = (double)p.x - mx, dy = (double)p.y - my, dz = (double)p.z - mz;
+        cc[0] += dx * dx; cc[1] += dx * dy; cc[2] += dx * dz; cc[3] += dy * dy; cc[4] += dy * dz; cc[5] += dz * dz;
+        if (C.knn_out) C.knn_out[(size_t)self * k + u] = __float_as_int(p.w);
+      }
+      if (C.cov6) {
+        #pragma unroll
+        for (int t = 0; t < 6; t++) cc[t] /= (double)k;
+        double out[6];
+        regularize(cc, method, out);
+        store_cov6(C.cov6, self, out);
+      }
+    } else {
+      const int slot = atomicAdd(fail, 1);
+      fail[2 + 2 * slot] = cloud; fail[3 + 2 * slot] = j;
+    }
+  }
+  __syncwarp();
+  }   // persistent chunk loop
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exact kNN of ONE query by a whole warp (k <= 32): the fallback behind the chunk kernel.
+//  * lanes 0..26 each locate one cell of the 3x3x3 block around the query at level L (two binary searches in parallel);
+//    a warp scan of the cell counts gives the candidate total, which also steers the level: too many candidates -> finer
+//    level, fewer than k -> coarser, before anything is scanned;
+//  * candidates are scanned 32 at a time (coalesced), the current top-32 lives one element per lane, sorted
+//    by (distance, index); a batch in which nobody beats the k-th distance costs one ballot; otherwise the
+//    winners are inserted by shuffle (few) or the batch is bitonic-sorted and merged (many);
+//  * the result is exact once the k-th distance is inside the radius the scanned block provably covers, else one level coarser.
+// Returns this lane's element of the ascending (distance, index) list (KEY_INF = none).
+// ---------------------------------------------------------------------------------------------------
+constexpr int KNN_CAND_CAP = 1024;    // prefer a finer level when the block holds more candidates than this
+
+__device__ unsigned long long knn_warp_query(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes,
+                                             const int* __restrict__ bucket_start, int n, int k, const Quant& qn, int j, const float4 q) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const Quant qn = make_quant(bbox);
-
-  // ranges of the previous query of this warp: consecutive Morton neighbours usually share the block
-  int prevL = -1, prev_cx = 0, prev_cy = 0, prev_cz = 0, lo = 0, cnt = 0, incl = 0, total = 0;
-
-  #pragma unroll 1
-  for (int qq = 0; qq < KNN_QPW; qq++) {
-    const int j = warp_global * KNN_QPW + qq;
-    if (j >= n) break;                                   // warp-uniform
-    const float4 q = __ldg(sorted + j);
-    const int self = __float_as_int(q.w);
-    const unsigned long long cq = __ldg(codes + j);
-    const unsigned long long cc3 = __ldg(cells + j);
-    const unsigned ix = (unsigned)(cc3 & 0x1FFFFFull), iy = (unsigned)((cc3 >> 21) & 0x1FFFFFull), iz = (unsigned)(cc3 >> 42);
-
-    // start level: reuse the previous query's final level when this query lies in the same cell there; otherwise
+  unsigned ix, iy, iz;
+  quantize(qn, q.x, q.y, q.z, ix, iy, iz);
+  const unsigned long long cq = __ldg(codes + j);
+  int L;
+  {
     // the level-cpl(code[j], code[j-4]) cell holds the sorted entries j-4..j (likewise on the right), so the
     // larger of the two common prefixes is a boundary-robust first guess
-    int L;
-    bool reuse = false;
-    if (prevL >= 0 && (int)(ix >> (MORTON_BITS - prevL)) == prev_cx && (int)(iy >> (MORTON_BITS - prevL)) == prev_cy &&
-        (int)(iz >> (MORTON_BITS - prevL)) == prev_cz) {
-      L = prevL; reuse = true;
-    } else {
-      const unsigned long long xl = cq ^ __ldg(codes + max(j - 4, 0)), xr = cq ^ __ldg(codes + min(j + 4, n - 1));
-      const int bl = (j - 4 >= 0) ? (xl ? (__clzll((long long)xl) - (64 - CODE_BITS)) : CODE_BITS) : 0;
-      const int br = (j + 4 < n) ? (xr ? (__clzll((long long)xr) - (64 - CODE_BITS)) : CODE_BITS) : 0;
-      L = min(max(bl, br) / 3, MORTON_BITS);
+    const unsigned long long xl = cq ^ __ldg(codes + max(j - 4, 0)), xr = cq ^ __ldg(codes + min(j + 4, n - 1));
+    const int bl = (j - 4 >= 0) ? (xl ? (__clzll((long long)xl) - (64 - CODE_BITS)) : CODE_BITS) : 0;
+    const int br = (j + 4 < n) ? (xr ? (__clzll((long long)xr) - (64 - CODE_BITS)) : CODE_BITS) : 0;
+    L = min(max(bl, br) / 3, MORTON_BITS);
+  }
+  unsigned long long top = KEY_INF;                   // this lane's element of the sorted top-32
+  bool no_finer = false;
+  #pragma unroll 1
+  for (;;) {
+    const int sh = MORTON_BITS - L;
+    const int cx = (int)(ix >> sh), cy = (int)(iy >> sh), cz = (int)(iz >> sh);
+    const int ncell = 1 << L;
+    int lo = 0, cnt = 0;
+    if (lane < 27) {
+      const int oo = (lane == 0) ? 13 : (lane <= 13 ? lane - 1 : lane);   // centre cell first
+      const int nx = cx + oo % 3 - 1, ny = cy + (oo / 3) % 3 - 1, nz = cz + oo / 9 - 1;
+      if (nx >= 0 && ny >= 0 && nz >= 0 && nx < ncell && ny < ncell && nz < ncell) {
+        const unsigned long long pre = morton3((unsigned)nx, (unsigned)ny, (unsigned)nz);
+        lo = lower_bound_bucketed(codes, bucket_start, pre << (3 * sh));
+        const int hi = (L == 0) ? n : lower_bound_bucketed(codes, bucket_start, (pre + 1ull) << (3 * sh));
+        cnt = hi - lo;
+      }
     }
+    int incl = cnt;
+    #pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (!no_finer && total > KNN_CAND_CAP && L < MORTON_BITS) { L++; continue; }
+    if (total < k && L > 0) { no_finer = true; L--; continue; }
+    const int excl = incl - cnt;
 
-    unsigned long long top = KEY_INF;                   // this lane's element of the sorted top-32
-    bool no_finer = reuse;
+    top = KEY_INF;
     #pragma unroll 1
-    for (;;) {
-      const int sh = MORTON_BITS - L;
-      const int cx = (int)(ix >> sh), cy = (int)(iy >> sh), cz = (int)(iz >> sh);
-      const int ncell = 1 << L;
-      if (!reuse) {
-        lo = 0; cnt = 0;
-        if (lane < 27) {
-          const int oo = (lane == 0) ? 13 : (lane <= 13 ? lane - 1 : lane);   // centre cell first
-          const int nx = cx + oo % 3 - 1, ny = cy + (oo / 3) % 3 - 1, nz = cz + oo / 9 - 1;
-          if (nx >= 0 && ny >= 0 && nz >= 0 && nx < ncell && ny < ncell && nz < ncell) {
-            const unsigned long long pre = morton3((unsigned)nx, (unsigned)ny, (unsigned)nz);
-            lo = lower_bound_bucketed(codes, bucket_start, pre << (3 * sh));
-            const int hi = (L == 0) ? n : lower_bound_bucketed(codes, bucket_start, (pre + 1ull) << (3 * sh));
-            cnt = hi - lo;
-          }
-        }
-        incl = cnt;
-        #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
-        total = __shfl_sync(FULL, incl, 31);
-        if (!no_finer && total > KNN_CAND_CAP && L < MORTON_BITS) { L++; continue; }
-        if (total < k && L > 0) { no_finer = true; L--; continue; }
-      }
-      reuse = false;
-      prevL = L; prev_cx = cx; prev_cy = cy; prev_cz = cz;
-      const int excl = incl - cnt;
-
-      top = KEY_INF;
-      #pragma unroll 1
-      for (int base = 0; base < total; base += 32) {
-        const int g = base + lane;
-        const bool valid = g < total;
-        // owning cell: the first lane whose inclusive count exceeds g
-        int a = 0, b = 26;
-        #pragma unroll
-        for (int s = 0; s < 5; s++) {
-          const int mid = (a + b) >> 1;
-          const int v = __shfl_sync(FULL, incl, mid);
-          if (v <= g) a = mid + 1; else b = mid;
-        }
-        a = min(a, 26);
-        const int cell_lo = __shfl_sync(FULL, lo, a), cell_ex = __shfl_sync(FULL, excl, a);
-        unsigned long long key = KEY_INF;
-        if (valid) {
-          const float4 p = __ldg(sorted + cell_lo + (g - cell_ex));
-          const float dx = q.x - p.x, dy = q.y - p.y, dz = q.z - p.z;
-          float d = __fmul_rn(dx, dx);
-          d = __fadd_rn(d, __fmul_rn(dy, dy));
-          d = __fadd_rn(d, __fmul_rn(dz, dz));
-          key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
-        }
-        const unsigned long long kth = __shfl_sync(FULL, top, k - 1);
-        const bool pass = key < kth;
-        unsigned m = __ballot_sync(FULL, pass);
-        if (m == 0) continue;
-        if (__popc(m) > 10) {
-          // bitonic sort of the batch (non-passing lanes carry +inf), then bitonic merge with the top-32
-          if (!pass) key = KEY_INF;
-          #pragma unroll
-          for (int k2 = 2; k2 <= 32; k2 <<= 1) {
-            #pragma unroll
-            for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) bitonic_cmpx(key, j2, ((lane & k2) == 0) == ((lane & j2) == 0));
-          }
-          if (base == 0) {
-            top = key;                                   // the top-32 is still empty: the sorted batch is the new top-32
-          } else {
-            const unsigned long long rev = __shfl_sync(FULL, key, 31 - lane);
-            if (rev < top) top = rev;
-            #pragma unroll
-            for (int j2 = 16; j2 > 0; j2 >>= 1) bitonic_cmpx(top, j2, (lane & j2) == 0);
-          }
-        } else {
-          while (m) {
-            const int srcl = __ffs(m) - 1;
-            m &= m - 1;
-            const unsigned long long ck = __shfl_sync(FULL, key, srcl);
-            const int pos = __popc(__ballot_sync(FULL, top < ck));      // elements that stay in front
-            const unsigned long long up = __shfl_up_sync(FULL, top, 1);
-            if (lane > pos) top = up; else if (lane == pos) top = ck;
-          }
-        }
-      }
-      if (L == 0) break;
-      // exact iff the k-th neighbour lies inside the guaranteed-complete radius of the scanned block
-      const double sL = qn.cell * (double)(1 << sh);
-      const double rel[3] = {(double)q.x - qn.mn[0], (double)q.y - qn.mn[1], (double)q.z - qn.mn[2]};
-      double rs = 1e300;
-      const int cc[3] = {cx, cy, cz};
+    for (int base = 0; base < total; base += 32) {
+      const int g = base + lane;
+      const bool valid = g < total;
+      int a = 0, b = 26;                                // owning cell: the first lane whose inclusive count exceeds g
       #pragma unroll
-      for (int dd = 0; dd < 3; dd++) {
-        if (cc[dd] - 1 >= 0) rs = fmin(rs, rel[dd] - (double)(cc[dd] - 1) * sL);
-        if (cc[dd] + 1 < ncell) rs = fmin(rs, (double)(cc[dd] + 2) * sL - rel[dd]);
+      for (int s = 0; s < 5; s++) {
+        const int mid = (a + b) >> 1;
+        const int v = __shfl_sync(FULL, incl, mid);
+        if (v <= g) a = mid + 1; else b = mid;
+      }
+      a = min(a, 26);
+      const int cell_lo = __shfl_sync(FULL, lo, a), cell_ex = __shfl_sync(FULL, excl, a);
+      unsigned long long key = KEY_INF;
+      if (valid) {
+        const float4 p = __ldg(sorted + cell_lo + (g - cell_ex));
+        const float d = dist2_exact(q, p);
+        if (d == d) key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
       }
       const unsigned long long kth = __shfl_sync(FULL, top, k - 1);
-      if (kth != KEY_INF && (double)__uint_as_float((unsigned)(kth >> 32)) <= rs * rs * (1.0 - 1e-6)) break;
-      no_finer = true;
-      L--;
+      const bool pass = key < kth;
+      unsigned m = __ballot_sync(FULL, pass);
+      if (m == 0) continue;
+      if (__popc(m) > 10) {
+        // bitonic sort of the batch (non-passing lanes carry +inf), then bitonic merge with the top-32
+        if (!pass) key = KEY_INF;
+        #pragma unroll
+        for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+          #pragma unroll
+          for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) bitonic_cmpx(key, j2, ((lane & k2) == 0) == ((lane & j2) == 0));
+        }
+        if (base == 0) {
+          top = key;                                   // the top-32 is still empty: the sorted batch is the new top-32
+        } else {
+          const unsigned long long rev = __shfl_sync(FULL, key, 31 - lane);
+          if (rev < top) top = rev;
+          #pragma unroll
+          for (int j2 = 16; j2 > 0; j2 >>= 1) bitonic_cmpx(top, j2, (lane & j2) == 0);
+        }
+      } else {
+        while (m) {
+          const int srcl = __ffs(m) - 1;
+          m &= m - 1;
+          const unsigned long long ck = __shfl_sync(FULL, key, srcl);
+          const int pos = __popc(__ballot_sync(FULL, top < ck));      // elements that stay in front
+          const unsigned long long up = __shfl_up_sync(FULL, top, 1);
+          if (lane > pos) top = up; else if (lane == pos) top = ck;
+        }
+      }
     }
-    if (lane < k) knn_out[(size_t)self * k + lane] = (int)(unsigned)(top & 0xFFFFFFFFull);
+    if (L == 0) break;
+    // exact iff the k-th neighbour lies inside the guaranteed-complete radius of the scanned block
+    const double sL = qn.cell * (double)(1 << sh);
+    const double rel[3] = {(double)q.x - qn.mn[0], (double)q.y - qn.mn[1], (double)q.z - qn.mn[2]};
+    double rs = 1e300;
+    const int cc[3] = {cx, cy, cz};
+    #pragma unroll
+    for (int dd = 0; dd < 3; dd++) {
+      if (cc[dd] - 1 >= 0) rs = fmin(rs, rel[dd] - (double)(cc[dd] - 1) * sL);
+      if (cc[dd] + 1 < ncell) rs = fmin(rs, (double)(cc[dd] + 2) * sL - rel[dd]);
+    }
+    const unsigned long long kth = __shfl_sync(FULL, top, k - 1);
+    if (kth != KEY_INF && (double)__uint_as_float((unsigned)(kth >> 32)) <= rs * rs * (1.0 - 1e-6)) break;
+    no_finer = true;
+    L--;
+  }
+  return top;
+}
+
+// The queries the chunk kernel could not finish (fail list), one warp each: exact search, then the same covariance epilogue with the
+// k neighbours held one per lane (fp64 sums by butterfly). A query without k valid neighbours (non-finite coordinates) gets a
+// zero covariance (such a point never finds a voxel, so the value is never used).
+__global__ void __launch_bounds__(256)
+knn_fallback_kernel(const KnnCloud* __restrict__ clouds, const float4* __restrict__ sorted_all, const unsigned long long* __restrict__ codes_all,
+                    const int* __restrict__ bucket_all, const int* __restrict__ bbox_all, const int* __restrict__ fail, int k, int method) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int nfail = fail[0];
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  #pragma unroll 1
+  for (int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < nfail; e += warps_total) {
+    const int cloud = fail[2 + 2 * e], j = fail[3 + 2 * e];
+    const KnnCloud C = clouds[cloud];
+    const float4* __restrict__ sorted = sorted_all + C.off;
+    const Quant qn = make_quant(bbox_all + cloud * 8);
+    const float4 q = __ldg(sorted + j);
+    const int self = __float_as_int(q.w);
+    const unsigned long long top = knn_warp_query(sorted, codes_all + C.off, bucket_all + (size_t)cloud * (N_BUCKETS + 1), C.n, k, qn, j, q);
+    const bool mine = lane < k;
+    const unsigned idx = (unsigned)(top & 0xFFFFFFFFull);
+    const bool good = !mine || (top != KEY_INF && idx < (unsigned)C.n);
+    const bool all_good = __all_sync(FULL, good);
+    double v[3] = {0, 0, 0};
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (mine && all_good) { p = __ldg(C.pts + idx); v[0] = (double)p.x; v[1] = (double)p.y; v[2] = (double)p.z; }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      #pragma unroll
+      for (int t = 0; t < 3; t++) v[t] += __shfl_xor_sync(FULL, v[t], o);
+    }
+    double cc[6] = {0, 0, 0, 0, 0, 0};
+    if (mine && all_good) {
+      const double dx = (double)p.x - v[0] / k, dy = (double)p.y - v[1] / k, dz = (double)p.z - v[2] / k;
+      cc[0] = dx * dx; cc[1] = dx * dy; cc[2] = dx * dz; cc[3] = dy * dy; cc[4] = dy * dz; cc[5] = dz * dz;
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      #pragma unroll
+      for (int t = 0; t < 6; t++) cc[t] += __shfl_xor_sync(FULL, cc[t], o);
+    }
+    if (C.knn_out && mine) C.knn_out[(size_t)self * k + lane] = all_good ? (int)idx : -1;
+    if (C.cov6 && lane == 0) {
+      double out[6];
+      if (all_good) {
+        #pragma unroll
+        for (int t = 0; t < 6; t++) cc[t] /= (double)k;
+        regularize(cc, method, out);
+      } else {
+        #pragma unroll
+        for (int t = 0; t < 6; t++) out[t] = 0.0;
+      }
+      store_cov6(C.cov6, self, out);
+    }
   }
 }
 
@@ -543,26 +925,29 @@ cov_from_knn_kernel(const float4* __restrict__ pts, const int* __restrict__ knn,
 
 size_t cov_bucket_table_entries() { return (size_t)N_BUCKETS + 1; }
 
-size_t cov_cub_temp_bytes(int n) {
+static int cloud_bits(int n_clouds) { int b = 0; while ((1 << b) < n_clouds) b++; return b; }
+
+size_t cov_cub_temp_bytes(int n, int n_clouds) {
   size_t bytes = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
-                                  (const int*)nullptr, (int*)nullptr, n, 0, 3 * MORTON_BITS);
+                                  (const int*)nullptr, (int*)nullptr, n, 0, CODE_BITS + cloud_bits(n_clouds));
   return bytes;
 }
 
-// bounding box -> Morton codes -> radix sort -> Morton-ordered copy (+ bucket table): the spatial index shared by the
-// covariance kNN and the scan-to-map 5-NN (scan2map.cu)
+// bounding box -> Morton codes -> radix sort -> Morton-ordered copy (+ bucket table) of ONE cloud: the spatial index of the
+// scan-to-map 5-NN (scan2map.cu), the fitness score and the generic k > 32 path
 cudaError_t launch_sort_cloud(const float4* pts, int n, const CovScratch& s, bool bucket_table, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   const int tb = 256, nb = (n + tb - 1) / tb;
-  bbox_init_kernel<<<1, 32, 0, stream>>>(s.bbox);
-  bbox_kernel<<<min(nb, 148), tb, 0, stream>>>(pts, n, s.bbox);
-  morton_kernel<<<nb, tb, 0, stream>>>(pts, n, s.bbox, s.codes_in, s.idx_in);
+  CloudRef ref; ref.arr = nullptr; ref.one.pts = pts; ref.one.cov6 = nullptr; ref.one.knn_out = nullptr; ref.one.n = n; ref.one.off = 0; ref.one.chunk_off = 0;
+  bbox_init_kernel<<<1, 32, 0, stream>>>(s.bbox, 1);
+  bbox_kernel<<<min(nb, 148), tb, 0, stream>>>(ref, s.bbox);
+  morton_kernel<<<nb, tb, 0, stream>>>(ref, s.bbox, s.codes_in, s.idx_in);
   size_t temp = s.cub_temp_bytes;
-  cudaError_t e = cub::DeviceRadixSort::SortPairs(s.cub_temp, temp, s.codes_in, s.codes_out, s.idx_in, s.idx_out, n, 0, 3 * MORTON_BITS, stream);
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(s.cub_temp, temp, s.codes_in, s.codes_out, s.idx_in, s.idx_out, n, 0, CODE_BITS, stream);
   if (e != cudaSuccess) return e;
-  gather_sorted_kernel<<<nb, tb, 0, stream>>>(pts, s.idx_out, n, s.bbox, s.sorted, s.codes_in);   // codes_in now holds the packed cell coordinates
-  if (bucket_table) bucket_table_kernel<<<(N_BUCKETS + 1 + tb - 1) / tb, tb, 0, stream>>>(s.codes_out, n, s.bucket_start);
+  gather_sorted_kernel<<<nb, tb, 0, stream>>>(ref, s.idx_out, s.codes_out, s.sorted, nullptr);
+  if (bucket_table) bucket_table_kernel<<<(N_BUCKETS + 1 + tb - 1) / tb, tb, 0, stream>>>(ref, s.codes_out, s.bucket_start);
   return cudaGetLastError();
 }
 
@@ -573,20 +958,62 @@ cudaError_t launch_nearest(const float4* queries, int nq, const float* T12_dev, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_covariances(const CovLaunch& L, cudaStream_t stream) {
+cudaError_t launch_covariances_generic(const CovLaunch& L, cudaStream_t stream) {
   if (L.n <= 0) return cudaSuccess;
   if (L.k > KCAP || L.k < 1 || L.n < L.k || !L.knn) return cudaErrorInvalidValue;
   const int n = L.n;
-  cudaError_t e = launch_sort_cloud(L.pts, n, L.s, L.k <= 32, stream);
+  cudaError_t e = launch_sort_cloud(L.pts, n, L.s, false, stream);
   if (e != cudaSuccess) return e;
-  if (L.k <= 32) {
-    const int queries_per_block = (256 / 32) * KNN_QPW;
-    const int gb = (n + queries_per_block - 1) / queries_per_block;
-    knn_warp_kernel<<<gb, 256, 0, stream>>>(L.s.sorted, L.s.codes_out, L.s.codes_in, L.s.bucket_start, n, L.k, L.s.bbox, L.knn);
-  } else {
-    knn_thread_kernel<<<(n + 127) / 128, 128, 0, stream>>>(L.s.sorted, L.s.codes_out, n, L.k, L.s.bbox, L.knn);
-  }
+  knn_thread_kernel<<<(n + 127) / 128, 128, 0, stream>>>(L.s.sorted, L.s.codes_out, n, L.k, L.s.bbox, L.knn);
   if (L.cov6) cov_from_knn_kernel<<<(n + 127) / 128, 128, 0, stream>>>(L.pts, L.knn, n, L.k, L.method, L.cov6);
+  return cudaGetLastError();
+}
+
+template <int KC>
+static cudaError_t launch_chunk(const KnnGroup& g, int total_chunks, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(knn_chunk_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)KNN_SMEM);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = std::max(1, std::min(2 * sms, (total_chunks + KNN_WARPS - 1) / KNN_WARPS));   // 2 resident CTAs per SM
+  knn_chunk_kernel<KC><<<grid, KNN_WARPS * 32, KNN_SMEM, stream>>>(g.s.clouds, g.n_clouds, total_chunks, g.s.sorted, g.s.codes_a, g.s.bucket_start, g.s.bbox,
+                                                                    g.s.fail, g.k, g.method, g.stats);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_covariances_group(const KnnGroup& g, cudaStream_t stream, int* own_launches) {
+  if (own_launches) *own_launches = 0;
+  if (g.n_clouds <= 0 || g.total <= 0) return cudaSuccess;
+  if (g.k < 1 || g.k > 32 || g.n_clouds > KNN_MAX_CLOUDS) return cudaErrorInvalidValue;
+  for (int c = 0; c < g.n_clouds; c++) if (g.clouds[c].n < g.k) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemcpyAsync(g.s.clouds, g.clouds, sizeof(KnnCloud) * g.n_clouds, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(g.s.fail, 0, 2 * sizeof(int), stream)) != cudaSuccess) return e;
+  const int tb = 256;
+  const unsigned nc = (unsigned)g.n_clouds;
+  const unsigned nb = (unsigned)((g.max_n + tb - 1) / tb);
+  CloudRef ref; ref.arr = g.s.clouds; ref.one = g.clouds[0];
+  bbox_init_kernel<<<(g.n_clouds * 8 + tb - 1) / tb, tb, 0, stream>>>(g.s.bbox, g.n_clouds);
+  bbox_kernel<<<dim3(max(1u, min(nb, 1184u / nc)), nc), tb, 0, stream>>>(ref, g.s.bbox);
+  morton_kernel<<<dim3(nb, nc), tb, 0, stream>>>(ref, g.s.bbox, g.s.codes_a, g.s.idx_a);
+  size_t temp = g.s.cub_temp_bytes;
+  e = cub::DeviceRadixSort::SortPairs(g.s.cub_temp, temp, g.s.codes_a, g.s.codes_b, g.s.idx_a, g.s.idx_b, g.total, 0, CODE_BITS + cloud_bits(g.n_clouds), stream);
+  if (e != cudaSuccess) return e;
+  gather_sorted_kernel<<<dim3(nb, nc), tb, 0, stream>>>(ref, g.s.idx_b, g.s.codes_b, g.s.sorted, g.s.codes_a);
+  bucket_table_kernel<<<dim3((N_BUCKETS + 1 + tb - 1) / tb, nc), tb, 0, stream>>>(ref, g.s.codes_a, g.s.bucket_start);
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  int total_chunks = 0;
+  for (int c = 0; c < g.n_clouds; c++) total_chunks += (g.clouds[c].n + 31) / 32;   // == the chunk_off prefix the caller filled in
+  if (g.k <= 8) e = launch_chunk<8>(g, total_chunks, stream);
+  else if (g.k <= 12) e = launch_chunk<12>(g, total_chunks, stream);
+  else if (g.k <= 16) e = launch_chunk<16>(g, total_chunks, stream);
+  else if (g.k <= 20) e = launch_chunk<20>(g, total_chunks, stream);
+  else if (g.k <= 24) e = launch_chunk<24>(g, total_chunks, stream);
+  else e = launch_chunk<32>(g, total_chunks, stream);
+  if (e != cudaSuccess) return e;
+  knn_fallback_kernel<<<296, 256, 0, stream>>>(g.s.clouds, g.s.sorted, g.s.codes_a, g.s.bucket_start, g.s.bbox, g.s.fail, g.k, g.method);
+  if (own_launches) *own_launches = 7;   // bbox_init, bbox, morton, gather, bucket table, chunk kNN + covariance, fallback (+ 1 memset not counted; cub's kernels not counted)
   return cudaGetLastError();
 }
 

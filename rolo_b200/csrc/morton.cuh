@@ -1,6 +1,6 @@
 // morton.cuh — device helpers of the Morton-ordered spatial index (shared by covariance.cu and scan2map.cu).
 // A cloud is indexed by: its bounding box (ordered-int min/max), 39-bit Morton codes of the quantised coordinates, the
-// radix-sorted (code, index) pairs, a Morton-ordered copy of the points and a bucket table over the top 18 code bits.
+// radix-sorted (code, index) pairs, a Morton-ordered copy of the points and a bucket table over the top 15 code bits.
 // A level-L cell (L <= MORTON_BITS) is one contiguous range of the sorted codes, found by two binary searches.
 #pragma once
 #include <cuda_runtime.h>
@@ -61,7 +61,7 @@ __device__ __forceinline__ int lower_bound_u64(const unsigned long long* __restr
   return lo;
 }
 
-constexpr int BUCKET_BITS = 18;       // top Morton bits indexed by the bucket table (octree level 6)
+constexpr int BUCKET_BITS = 15;       // top Morton bits indexed by the bucket table (octree level 5): 128 KB per cloud, L2-resident for a whole group
 constexpr int BUCKET_SHIFT = 3 * MORTON_BITS - BUCKET_BITS;
 constexpr int N_BUCKETS = 1 << BUCKET_BITS;
 
@@ -70,7 +70,7 @@ __device__ __forceinline__ int lower_bound_bucketed(const unsigned long long* __
   const unsigned long long top = key >> BUCKET_SHIFT;
   if (top >= (unsigned long long)N_BUCKETS) return __ldg(bucket_start + N_BUCKETS);
   int lo = __ldg(bucket_start + top);
-  if ((key & ((1ull << BUCKET_SHIFT) - 1ull)) == 0ull) return lo;     // bucket-aligned key (levels <= 6)
+  if ((key & ((1ull << BUCKET_SHIFT) - 1ull)) == 0ull) return lo;     // bucket-aligned key (levels <= 5)
   int hi = __ldg(bucket_start + top + 1);
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;

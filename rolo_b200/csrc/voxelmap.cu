@@ -13,20 +13,44 @@
 // are not materialised.
 
 #include "voxelmap.cuh"
+#include <algorithm>
 
 namespace rolo {
 
 namespace {
 
-__global__ void vox_insert_kernel(const float4* __restrict__ pts, int n, GridParams grid, VoxSlot* table, unsigned mask,
-                                  int* __restrict__ slot_of_point, int* counters /* [0]=voxel count, [1]=error flag */,
-                                  double* __restrict__ sums, int pair_stride_unused) {
+// a build descriptor reaches the kernels either from a device array (batch: one per blockIdx.y) or by value
+struct BuildRef {
+  const VoxelBuild* arr;
+  VoxelBuild one;
+};
+__device__ __forceinline__ const VoxelBuild& get_build(const BuildRef& r) { return r.arr ? r.arr[blockIdx.y] : r.one; }
+
+__global__ void vox_clear_kernel(BuildRef ref) {
+  const VoxelBuild& B = get_build(ref);
+  const size_t cap = (size_t)B.mask + 1;
+  if (blockIdx.x == 0 && threadIdx.x < 2) B.counters[threadIdx.x] = 0;
+  ulonglong2* t = reinterpret_cast<ulonglong2*>(B.table);
+  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (size_t)gridDim.x * blockDim.x)
+    t[s] = make_ulonglong2(KEY_EMPTY, 0xFFFFFFFFFFFFFFFFull);
+}
+
+__global__ void vox_insert_kernel(BuildRef ref) {
+  const VoxelBuild& B = get_build(ref);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 p = pts[i];
+  if (i >= B.n) return;
+  VoxSlot* table = B.table;
+  const unsigned mask = B.mask;
+  int* counters = B.counters;
+  const float4 p = B.pts[i];
   int cx, cy, cz;
-  voxel_coord(grid, (double)p.x, (double)p.y, (double)p.z, cx, cy, cz);
-  if (!key_in_range(cx, cy, cz)) { atomicExch(&counters[1], 1); slot_of_point[i] = -1; return; }
+  voxel_coord(B.grid, (double)p.x, (double)p.y, (double)p.z, cx, cy, cz);
+  // a point without a finite key (NaN / Inf coordinates, the origin of a polar grid) sits in an unreachable cell of the
+  // reference's map (x86 converts the NaN to INT_MIN): it is simply not inserted
+  const bool finite = (p.x - p.x == 0.f) && (p.y - p.y == 0.f) && (p.z - p.z == 0.f) &&
+                      (B.grid.voxel_type != 0 || (p.x != 0.f || p.y != 0.f || p.z != 0.f));
+  if (!finite) { B.slot_of_point[i] = -1; return; }
+  if (!key_in_range(cx, cy, cz)) { atomicExch(&counters[1], 1); B.slot_of_point[i] = -1; return; }
   const unsigned long long key = pack_key(cx, cy, cz);
   unsigned h = hash_key(key) & mask;
   for (unsigned probe = 0; probe <= mask; probe++) {
@@ -37,23 +61,24 @@ __global__ void vox_insert_kernel(const float4* __restrict__ pts, int n, GridPar
       if (cur == KEY_EMPTY) {              // we created the voxel
         const int id = atomicAdd(&counters[0], 1);
         table[h].id = id;
-        double* row = sums + (size_t)id * 10;
+        double* row = B.sums + (size_t)id * 10;
         #pragma unroll
         for (int k = 0; k < 10; k++) row[k] = 0.0;
-        slot_of_point[i] = (int)h;
+        B.slot_of_point[i] = (int)h;
         return;
       }
     }
-    if (cur == key) { slot_of_point[i] = (int)h; return; }
+    if (cur == key) { B.slot_of_point[i] = (int)h; return; }
     h = (h + 1) & mask;
   }
   atomicExch(&counters[1], 2);   // table full (cannot happen with cap >= 2n)
-  slot_of_point[i] = -1;
+  B.slot_of_point[i] = -1;
 }
 
-__global__ void vox_accumulate_kernel(const float4* __restrict__ pts, const float* __restrict__ cov6, int n,
-                                      const int* __restrict__ slot_of_point, const VoxSlot* __restrict__ table,
-                                      double* __restrict__ sums) {
+__global__ void vox_accumulate_kernel(BuildRef ref) {
+  const VoxelBuild& B = get_build(ref);
+  const int n = B.n;
+  if ((int)(blockIdx.x * blockDim.x) >= n) return;          // block-uniform
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
   int id = -1;
@@ -61,14 +86,14 @@ __global__ void vox_accumulate_kernel(const float4* __restrict__ pts, const floa
   #pragma unroll
   for (int k = 0; k < 10; k++) v[k] = 0.0;
   if (i < n) {
-    const int slot = slot_of_point[i];
+    const int slot = B.slot_of_point[i];
     if (slot >= 0) {
-      id = table[slot].id;
-      const float4 p = pts[i];
+      id = B.table[slot].id;
+      const float4 p = B.pts[i];
       const size_t base = (size_t)(i / TILE_PTS) * COV_PLANES * TILE_PTS + (i % TILE_PTS);
       v[0] = (double)p.x; v[1] = (double)p.y; v[2] = (double)p.z;
       #pragma unroll
-      for (int c = 0; c < 6; c++) v[3 + c] = (double)cov6[base + (size_t)c * TILE_PTS];
+      for (int c = 0; c < 6; c++) v[3 + c] = (double)B.cov6[base + (size_t)c * TILE_PTS];
       v[9] = 1.0;
     }
   }
@@ -88,39 +113,57 @@ __global__ void vox_accumulate_kernel(const float4* __restrict__ pts, const floa
   const int nxt = __shfl_down_sync(0xffffffffu, id, 1);
   const bool tail = (lane == 31) || (nxt != id);
   if (tail && id >= 0) {
-    double* row = sums + (size_t)id * 10;
+    double* row = B.sums + (size_t)id * 10;
     #pragma unroll
     for (int k = 0; k < 10; k++) atomicAdd(row + k, v[k]);
   }
 }
 
-__global__ void vox_finalize_kernel(const double* __restrict__ sums, const int* __restrict__ counters, VoxPayload* __restrict__ vox, int max_v) {
+__global__ void vox_finalize_kernel(BuildRef ref) {
+  const VoxelBuild& B = get_build(ref);
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= max_v || id >= counters[0]) return;
-  const double* row = sums + (size_t)id * 10;
+  if (id >= B.n || id >= B.counters[0]) return;
+  const double* row = B.sums + (size_t)id * 10;
   const double cnt = row[9];
   VoxPayload p;
   p.mean[0] = row[0] / cnt; p.mean[1] = row[1] / cnt; p.mean[2] = row[2] / cnt;
   #pragma unroll
   for (int c = 0; c < 6; c++) p.cov[c] = row[3 + c] / cnt;
   p.w = sqrt(cnt);
-  vox[id] = p;
+  B.vox[id] = p;
+}
+
+cudaError_t launch_all(const BuildRef& ref, int n_builds, int max_n, unsigned max_mask, cudaStream_t stream) {
+  if (n_builds <= 0) return cudaSuccess;
+  const int threads = 256;
+  const unsigned nb = (unsigned)std::max(1, (max_n + threads - 1) / threads);
+  const size_t cap = (size_t)max_mask + 1;
+  const unsigned cb = (unsigned)std::min<size_t>((cap + threads - 1) / threads, 2048);
+  vox_clear_kernel<<<dim3(cb, n_builds), threads, 0, stream>>>(ref);
+  if (max_n > 0) {
+    vox_insert_kernel<<<dim3(nb, n_builds), threads, 0, stream>>>(ref);
+    vox_accumulate_kernel<<<dim3(nb, n_builds), threads, 0, stream>>>(ref);
+    vox_finalize_kernel<<<dim3(nb, n_builds), threads, 0, stream>>>(ref);
+  }
+  return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t launch_voxel_build(const VoxelBuild& b, cudaStream_t stream) {
-  cudaError_t e;
-  const size_t cap = (size_t)b.mask + 1;
-  if ((e = cudaMemsetAsync(b.table, 0xFF, cap * sizeof(VoxSlot), stream)) != cudaSuccess) return e;
-  if ((e = cudaMemsetAsync(b.counters, 0, 2 * sizeof(int), stream)) != cudaSuccess) return e;
-  if (b.n == 0) return cudaSuccess;
-  const int threads = 256;
-  const int blocks = (b.n + threads - 1) / threads;
-  vox_insert_kernel<<<blocks, threads, 0, stream>>>(b.pts, b.n, b.grid, b.table, b.mask, b.slot_of_point, b.counters, b.sums, 0);
-  vox_accumulate_kernel<<<blocks, threads, 0, stream>>>(b.pts, b.cov6, b.n, b.slot_of_point, b.table, b.sums);
-  vox_finalize_kernel<<<blocks, threads, 0, stream>>>(b.sums, b.counters, b.vox, b.n);
-  return cudaGetLastError();
+  BuildRef ref; ref.arr = nullptr; ref.one = b;
+  return launch_all(ref, 1, b.n, b.mask, stream);
+}
+
+// every target of a batch in one launch chain: `dev_builds` is the device copy of `host_builds`
+cudaError_t launch_voxel_build_batch(const VoxelBuild* host_builds, VoxelBuild* dev_builds, int n_builds, cudaStream_t stream) {
+  if (n_builds <= 0) return cudaSuccess;
+  int max_n = 0; unsigned max_mask = 0;
+  for (int i = 0; i < n_builds; i++) { max_n = std::max(max_n, host_builds[i].n); max_mask = std::max(max_mask, host_builds[i].mask); }
+  cudaError_t e = cudaMemcpyAsync(dev_builds, host_builds, sizeof(VoxelBuild) * n_builds, cudaMemcpyHostToDevice, stream);
+  if (e != cudaSuccess) return e;
+  BuildRef ref; ref.arr = dev_builds; ref.one = host_builds[0];
+  return launch_all(ref, n_builds, max_n, max_mask, stream);
 }
 
 }  // namespace rolo

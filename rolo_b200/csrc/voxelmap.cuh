@@ -17,6 +17,8 @@ struct VoxelBuild {
   VoxPayload* vox;         // out [<= n]
 };
 
-cudaError_t launch_voxel_build(const VoxelBuild& b, cudaStream_t stream);
+cudaError_t launch_voxel_build(const VoxelBuild& b, cudaStream_t stream);                                 // 4 kernels
+// every target cloud of a batch by the same 4 kernels on a (blocks, build) grid; dev_builds = device scratch [n_builds]
+cudaError_t launch_voxel_build_batch(const VoxelBuild* host_builds, VoxelBuild* dev_builds, int n_builds, cudaStream_t stream);
 
 }  // namespace rolo
