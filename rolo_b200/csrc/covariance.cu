@@ -26,6 +26,7 @@
 
 #include "covariance.cuh"
 #include "morton.cuh"
+#include "sort_networks.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <float.h>
@@ -242,16 +243,19 @@ __device__ __forceinline__ void store_cov6(float* __restrict__ cov6, int i, cons
 // chunk-cooperative exact kNN + covariance (see the file header). KC = compile-time capacity of the distance chain (k <= KC).
 // ---------------------------------------------------------------------------------------------------
 constexpr int KNN_WARPS = 8;          // warps (= chunks of 32 queries) per CTA; warps are independent (no CTA barrier)
-constexpr int KNN_STAGE = 128;        // staged candidates per warp (float4)
-constexpr int KNN_PL = 64;            // pass-list entries per lane
-constexpr int KNN_PEND = 8;           // distances waiting for the chain, per lane
+constexpr int KNN_STAGE = 128;        // staged candidates per warp (float4), + 4 entries of padding
+constexpr int KNN_PL = 28;            // per-lane list of (position, distance): a window phase queues <= 22 distances, the region phase
+                                      // records the candidates within the window's k-th distance
 constexpr int KNN_TIE = 16;           // tie entries per lane (aliases the stage buffer: 128 float4 = 16 x 32 ints)
-constexpr int KNN_RAW_CAP = 3072;      // candidates of one group before clipping; above it the widest lanes go to the fallback kernel
+constexpr int KNN_RAW_CAP = 3072;     // candidates of one group before clipping; above it the widest lanes go to the fallback kernel
 constexpr int KNN_WINDOW = 64;        // Morton-order neighbours scanned first (the chunk itself + 16 before + 16 after)
-constexpr size_t KNN_SMEM_WARP = KNN_STAGE * sizeof(float4) + (size_t)KNN_PL * 32 * sizeof(int) + (size_t)KNN_PEND * 32 * sizeof(float);
-constexpr size_t KNN_SMEM = (size_t)KNN_WARPS * KNN_SMEM_WARP;
+constexpr int KNN_FILL = 20;          // window entries visited before the first list update (every lane's nearest Morton neighbours)
+constexpr size_t KNN_STAGE_BYTES = (KNN_STAGE + 4) * sizeof(float4);
+constexpr size_t KNN_SMEM_WARP = KNN_STAGE_BYTES + (size_t)KNN_PL * 32 * (sizeof(int) + sizeof(float));
+constexpr size_t KNN_SMEM = KNN_WARPS * KNN_SMEM_WARP;
 static_assert(KNN_TIE * 32 * sizeof(int) <= KNN_STAGE * sizeof(float4), "tie buffer aliases the stage buffer");
-static_assert(KNN_WINDOW <= KNN_STAGE, "the window is staged as one tile");
+static_assert(KNN_WINDOW <= KNN_STAGE && (KNN_WINDOW & (KNN_WINDOW - 1)) == 0, "the window is staged as one tile and indexed modulo its size");
+static_assert((KNN_WINDOW - KNN_FILL + 1) / 2 <= KNN_PL && KNN_FILL <= KNN_PL && 2 * KNN_PL >= 32, "list capacity");
 
 template <int KC>
 __device__ __forceinline__ void chain_insert(float (&a)[KC], float v) {
@@ -261,72 +265,20 @@ __device__ __forceinline__ void chain_insert(float (&a)[KC], float v) {
   a[0] = fminf(a[0], v);
 }
 
-// per-lane search state of the chunk kernel
 template <int KC>
-struct KnnLane {
-  float a[KC];                // ascending; a[KC-1] = k-th smallest distance seen (the low KC-k slots are pinned at -1)
-  int npass, npend;
-  bool overflow;
-};
-
-// chain update with every pending distance (all lanes in lock step), then, if a pass list is nearly full, drop its entries that
-// fell behind the running k-th distance
-template <int KC>
-__device__ __forceinline__ void knn_flush(KnnLane<KC>& L, const float4 q, const float4* __restrict__ sorted, int* plist, const float* pend) {
-  const unsigned FULL = 0xffffffffu;
-  const int mx = __reduce_max_sync(FULL, L.npend);
-  #pragma unroll 1
-  for (int e = 0; e < mx; e++) chain_insert<KC>(L.a, e < L.npend ? pend[e * 32] : CUDART_INF_F);
-  L.npend = 0;
-  if (__any_sync(FULL, L.npass > KNN_PL - 2 * KNN_PEND)) {
-    const float cur = L.a[KC - 1];
-    const int have = min(L.npass, KNN_PL);
-    int m2 = 0;
-    #pragma unroll 1
-    for (int e = 0; e < have; e++) {
-      const int pos = plist[e * 32];
-      if (dist2_exact(q, __ldg(sorted + pos)) <= cur) { plist[m2 * 32] = pos; m2++; }
-    }
-    if (L.npass > KNN_PL) L.overflow = true;               // entries were dropped before this prune
-    L.npass = m2;
-    if (L.npass > KNN_PL - 2 * KNN_PEND) L.overflow = true;   // that many candidates inside the k-th distance: exact ties en masse
-  }
-}
-
-// every lane of the group scans the `ns` staged candidates (ns even; a padding entry has NaN coordinates)
-template <int KC>
-__device__ __forceinline__ void knn_scan_tile(KnnLane<KC>& L, const bool act, const float4 q, const float4* __restrict__ stage, int ns,
-                                              const float4* __restrict__ sorted, int* plist, float* pend, unsigned& st_events) {
-  const unsigned FULL = 0xffffffffu;
-  #pragma unroll 1
-  for (int s = 0; s < ns; s += 2) {
-    const float4 p0 = stage[s], p1 = stage[s + 1];          // broadcast reads
-    const float d0 = dist2_exact(q, p0), d1 = dist2_exact(q, p1);
-    const float thr = L.a[KC - 1];
-    const bool pass0 = act && d0 <= thr, pass1 = act && d1 <= thr;
-    if (__any_sync(FULL, pass0 || pass1)) {
-      st_events++;
-      if (pass0) { if (L.npass < KNN_PL) plist[L.npass * 32] = __float_as_int(p0.w); L.npass++; pend[L.npend * 32] = d0; L.npend++; }
-      if (pass1) { if (L.npass < KNN_PL) plist[L.npass * 32] = __float_as_int(p1.w); L.npass++; pend[L.npend * 32] = d1; L.npend++; }
-      if (__any_sync(FULL, L.npend >= KNN_PEND - 1)) knn_flush<KC>(L, q, sorted, plist, pend);
-    }
-  }
-  knn_flush<KC>(L, q, sorted, plist, pend);
-}
-
-template <int KC>
-__global__ void __launch_bounds__(KNN_WARPS * 32, 2)
+__global__ void __launch_bounds__(KNN_WARPS * 32, 3)
 knn_chunk_kernel(const KnnCloud* __restrict__ clouds, int n_clouds, int total_chunks, const float4* __restrict__ sorted_all,
                  const unsigned long long* __restrict__ codes_all, const int* __restrict__ bucket_all, const int* __restrict__ bbox_all,
                  int* __restrict__ fail, int k, int method, unsigned long long* stats) {
   extern __shared__ __align__(16) unsigned char knn_smem[];
   const unsigned FULL = 0xffffffffu;
+  const float INF = CUDART_INF_F;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* wsm = knn_smem + (size_t)warp * KNN_SMEM_WARP;
   float4* stage = reinterpret_cast<float4*>(wsm);
-  int* plist = reinterpret_cast<int*>(wsm + KNN_STAGE * sizeof(float4)) + lane;                                         // [slot * 32]
-  float* pend = reinterpret_cast<float*>(wsm + KNN_STAGE * sizeof(float4) + (size_t)KNN_PL * 32 * sizeof(int)) + lane;  // [slot * 32]
-  int* tie = reinterpret_cast<int*>(stage) + lane;                                                                      // [slot * 32]
+  int* pl_pos = reinterpret_cast<int*>(wsm + KNN_STAGE_BYTES) + lane;                                           // [slot * 32]
+  float* pl_d = reinterpret_cast<float*>(wsm + KNN_STAGE_BYTES + (size_t)KNN_PL * 32 * sizeof(int)) + lane;     // [slot * 32]
+  int* tie = reinterpret_cast<int*>(stage) + lane;                                                                         // [slot * 32]
 
   // persistent warps: the work per chunk varies by orders of magnitude (sparse far returns, chunks that straddle a jump of the
   // Morton curve), so every warp draws its next chunk from a global ticket instead of owning a fixed one
@@ -352,165 +304,267 @@ knn_chunk_kernel(const KnnCloud* __restrict__ clouds, int n_clouds, int total_ch
   const int j = j0 + lane;
   const bool in_cloud = j < n;
   const float4 q = __ldg(sorted + min(j, n - 1));            // lanes past the end repeat the last point and write nothing
-  bool finite = (q.x - q.x == 0.f) && (q.y - q.y == 0.f) && (q.z - q.z == 0.f);
+  const bool finite = (q.x - q.x == 0.f) && (q.y - q.y == 0.f) && (q.z - q.z == 0.f);
   bool kicked = false;                                       // handed to the fallback kernel (warp-per-query search)
+  bool overflow = false;
 
-  KnnLane<KC> L;
+  float a[KC];                                               // ascending; a[KC-1] = k-th smallest distance seen so far
   #pragma unroll
-  for (int i = 0; i < KC; i++) L.a[i] = (i < KC - k) ? -1.0f : CUDART_INF_F;   // the low KC-k slots are pinned below every distance
-  L.npass = 0; L.npend = 0; L.overflow = false;
+  for (int i = 0; i < KC; i++) a[i] = (i < KC - k) ? -1.0f : INF;   // the low KC-k slots are pinned below every distance
+  int npass = 0, nmerged = 0;                                // list entries; those below nmerged are already in `a`
+  unsigned long long wmask = 0;                              // window entries that were within the running k-th distance when visited
   unsigned st_staged = 0, st_events = 0, st_groups = 0, st_raw = 0;
 
-  // ---- a. the Morton-order neighbourhood of the chunk first: 64 candidates that bound every lane's k-th distance tightly
+  // the Morton-order neighbourhood of the chunk: 64 candidates, staged once
   const int wcnt = min(KNN_WINDOW, n);
   const int wlo = max(0, min(j0 - 16, n - wcnt));
-  {
-    #pragma unroll
-    for (int h = 0; h < KNN_WINDOW / 32; h++) {
-      const int w = h * 32 + lane;
-      float4 c = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, 0.f);
-      if (w < wcnt) { c = __ldg(sorted + wlo + w); c.w = __int_as_float(wlo + w); }
-      stage[w] = c;
-    }
-    __syncwarp();
-    knn_scan_tile<KC>(L, finite, q, stage, KNN_WINDOW, sorted, plist, pend, st_events);
-    __syncwarp();
+  #pragma unroll
+  for (int h = 0; h < KNN_WINDOW / 32; h++) {
+    const int w = h * 32 + lane;
+    float4 c = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, 0.f);
+    if (w < wcnt) c = __ldg(sorted + wlo + w);
+    stage[w] = c;
   }
+  __syncwarp();
 
-  // ---- b. search box of every lane (rounded outwards); consecutive lanes whose boxes are disjoint share no candidate, so the
-  //         chunk is cut there and the groups are searched one after the other (a chunk that straddles a jump of the Morton curve
-  //         would otherwise drag in everything between its two ends)
-  float l0, l1, l2, h0, h1, h2;
-  {
-    const float R = __fmul_ru(__fsqrt_ru(L.a[KC - 1]), 1.000001f);
-    l0 = __fsub_rd(q.x, R); l1 = __fsub_rd(q.y, R); l2 = __fsub_rd(q.z, R);
-    h0 = __fadd_ru(q.x, R); h1 = __fadd_ru(q.y, R); h2 = __fadd_ru(q.z, R);
-  }
-  unsigned cuts;
-  {
-    const float nl0 = __shfl_down_sync(FULL, l0, 1), nl1 = __shfl_down_sync(FULL, l1, 1), nl2 = __shfl_down_sync(FULL, l2, 1);
-    const float nh0 = __shfl_down_sync(FULL, h0, 1), nh1 = __shfl_down_sync(FULL, h1, 1), nh2 = __shfl_down_sync(FULL, h2, 1);
-    const bool nfin = __shfl_down_sync(FULL, finite ? 1 : 0, 1) != 0;
-    const bool overlap = nl0 <= h0 && l0 <= nh0 && nl1 <= h1 && l1 <= nh1 && nl2 <= h2 && l2 <= nh2;   // false for NaN boxes
-    cuts = __ballot_sync(FULL, lane < 31 && !(overlap && finite && nfin)) | 0x80000000u;
-  }
-  const Quant qn = make_quant(bbox_all + cloud * 8);
+  // Four phases, each ending in the same list update (one copy of the sorting network in the code):
+  //   0: every lane visits its 20 nearest Morton neighbours (j, j+1, j-1, j+2, ...): near in Morton order is mostly near in space,
+  //      so the first list is already good;
+  //   1, 2: the other 44 window entries in two halves, each against the fixed threshold of the phase before;
+  //   3: the candidates of the covering cells (the region), against the fixed threshold of phase 2: the lock-step scan only compares
+  //      and records, no list is touched inside it.
   #pragma unroll 1
-  for (int gstart = 0; gstart < 32;) {
-    const int gend = gstart + __ffs(cuts >> gstart) - 1;    // the group is lanes gstart..gend
-    const bool act = finite && lane >= gstart && lane <= gend;
-    gstart = gend + 1;
-    if (!__any_sync(FULL, act)) continue;
-    st_groups++;
-    const float INF = CUDART_INF_F;
-    float lox, loy, loz, hix, hiy, hiz;
-    int lo, cnt, incl, total, excl;
-    bool act_g = act;
-    #pragma unroll 1
-    for (int attempt = 0;; attempt++) {
-      lox = ordered_to_float(__reduce_min_sync(FULL, float_to_ordered(act_g ? l0 : INF)));
-      loy = ordered_to_float(__reduce_min_sync(FULL, float_to_ordered(act_g ? l1 : INF)));
-      loz = ordered_to_float(__reduce_min_sync(FULL, float_to_ordered(act_g ? l2 : INF)));
-      hix = ordered_to_float(__reduce_max_sync(FULL, float_to_ordered(act_g ? h0 : -INF)));
-      hiy = ordered_to_float(__reduce_max_sync(FULL, float_to_ordered(act_g ? h1 : -INF)));
-      hiz = ordered_to_float(__reduce_max_sync(FULL, float_to_ordered(act_g ? h2 : -INF)));
-      // covering cells: the finest level at which the box spans <= 32 cells; lane c looks up cell c (one range of the sorted array)
-      lo = 0; cnt = 0;
+  for (int phase = 0; phase < 4; phase++) {
+    if (phase < 3) {
+      const int wself = min(j, n - 1) - wlo;
+      const float thr = a[KC - 1];
+      const int tmid = KNN_FILL + (KNN_WINDOW - KNN_FILL) / 2;
+      const int t0 = phase == 0 ? 0 : (phase == 1 ? KNN_FILL : tmid), t1 = phase == 0 ? KNN_FILL : (phase == 1 ? tmid : KNN_WINDOW);
+      #pragma unroll 1
+      for (int t = t0; t < t1; t++) {
+        const int off = (t & 1) ? ((t + 1) >> 1) : -(t >> 1);
+        const int w = (wself + off) & (KNN_WINDOW - 1);
+        const float d = dist2_exact(q, stage[w]);
+        if (finite && d <= thr) { pl_d[npass * 32] = d; npass++; wmask |= 1ull << w; }
+      }
+    } else {
+      __syncwarp();                                          // the stage buffer is about to be reused
+      // ---- search box of every lane (rounded outwards); consecutive lanes whose boxes are disjoint share no candidate, so the chunk is
+      //      cut there and the groups are searched one after the other (a chunk that straddles a jump of the Morton curve would
+      //      otherwise drag in everything between its two ends)
+      const float thr = a[KC - 1];
+      float l0, l1, l2, h0, h1, h2;
       {
-        unsigned ix0, iy0, iz0, ix1, iy1, iz1;
-        quantize(qn, lox, loy, loz, ix0, iy0, iz0);
-        quantize(qn, hix, hiy, hiz, ix1, iy1, iz1);
-        const unsigned ext = max(max(ix1 - ix0, iy1 - iy0), iz1 - iz0);
-        int sh = max(0, 30 - __clz((int)ext));              // ext >> sh < 4
-        int ncx, ncy, ncz;
+        const float R = __fmul_ru(__fsqrt_ru(thr), 1.000001f);
+        l0 = __fsub_rd(q.x, R); l1 = __fsub_rd(q.y, R); l2 = __fsub_rd(q.z, R);
+        h0 = __fadd_ru(q.x, R); h1 = __fadd_ru(q.y, R); h2 = __fadd_ru(q.z, R);
+      }
+      unsigned cuts;
+      {
+        const float nl0 = __shfl_down_sync(FULL, l0, 1), nl1 = __shfl_down_sync(FULL, l1, 1), nl2 = __shfl_down_sync(FULL, l2, 1);
+        const float nh0 = __shfl_down_sync(FULL, h0, 1), nh1 = __shfl_down_sync(FULL, h1, 1), nh2 = __shfl_down_sync(FULL, h2, 1);
+        const bool nfin = __shfl_down_sync(FULL, finite ? 1 : 0, 1) != 0;
+        const bool overlap = nl0 <= h0 && l0 <= nh0 && nl1 <= h1 && l1 <= nh1 && nl2 <= h2 && l2 <= nh2;   // false for NaN boxes
+        cuts = __ballot_sync(FULL, lane < 31 && !(overlap && finite && nfin)) | 0x80000000u;
+      }
+      const Quant qn = make_quant(bbox_all + cloud * 8);
+      #pragma unroll 1
+      for (int gstart = 0; gstart < 32;) {
+        const int gend = gstart + __ffs(cuts >> gstart) - 1;    // the group is lanes gstart..gend
+        const bool act = finite && lane >= gstart && lane <= gend;
+        gstart = gend + 1;
+        if (!__any_sync(FULL, act)) continue;
+        st_groups++;
+        float lox, loy, loz, hix, hiy, hiz;
+        int lo, cnt, incl, total, excl;
+        bool act_g = act;
         #pragma unroll 1
-        for (;; sh++) {
-          ncx = (int)(ix1 >> sh) - (int)(ix0 >> sh) + 1; ncy = (int)(iy1 >> sh) - (int)(iy0 >> sh) + 1; ncz = (int)(iz1 >> sh) - (int)(iz0 >> sh) + 1;
-          if (ncx * ncy * ncz <= 32 || sh >= MORTON_BITS) break;
+        for (int attempt = 0;; attempt++) {
+          lox = ordered_to_float(__reduce_min_sync(FULL, float_to_ordered(act_g ? l0 : INF)));
+          loy = ordered_to_float(__reduce_min_sync(FULL, float_to_ordered(act_g ? l1 : INF)));
+          loz = ordered_to_float(__reduce_min_sync(FULL, float_to_ordered(act_g ? l2 : INF)));
+          hix = ordered_to_float(__reduce_max_sync(FULL, float_to_ordered(act_g ? h0 : -INF)));
+          hiy = ordered_to_float(__reduce_max_sync(FULL, float_to_ordered(act_g ? h1 : -INF)));
+          hiz = ordered_to_float(__reduce_max_sync(FULL, float_to_ordered(act_g ? h2 : -INF)));
+          // covering cells: the finest level at which the box spans <= 32 cells; lane c looks up cell c (one range of the sorted array)
+          lo = 0; cnt = 0;
+          {
+            unsigned ix0, iy0, iz0, ix1, iy1, iz1;
+            quantize(qn, lox, loy, loz, ix0, iy0, iz0);
+            quantize(qn, hix, hiy, hiz, ix1, iy1, iz1);
+            const unsigned ext = max(max(ix1 - ix0, iy1 - iy0), iz1 - iz0);
+            int sh = max(0, 30 - __clz((int)ext));          // ext >> sh < 4
+            int ncx, ncy, ncz;
+            #pragma unroll 1
+            for (;; sh++) {
+              ncx = (int)(ix1 >> sh) - (int)(ix0 >> sh) + 1; ncy = (int)(iy1 >> sh) - (int)(iy0 >> sh) + 1; ncz = (int)(iz1 >> sh) - (int)(iz0 >> sh) + 1;
+              if (ncx * ncy * ncz <= 32 || sh >= MORTON_BITS) break;
+            }
+            if (lane < ncx * ncy * ncz) {
+              const unsigned cx = (ix0 >> sh) + (unsigned)(lane % ncx), cy = (iy0 >> sh) + (unsigned)((lane / ncx) % ncy), cz = (iz0 >> sh) + (unsigned)(lane / (ncx * ncy));
+              const unsigned long long pre = morton3(cx, cy, cz);
+              lo = lower_bound_bucketed(codes, bucket_start, pre << (3 * sh));
+              const int hi = (sh >= MORTON_BITS) ? n : lower_bound_bucketed(codes, bucket_start, (pre + 1ull) << (3 * sh));
+              cnt = hi - lo;
+            }
+          }
+          incl = cnt;
+          #pragma unroll
+          for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
+          total = __shfl_sync(FULL, incl, 31);
+          excl = incl - cnt;
+          if (total <= KNN_RAW_CAP) break;
+          // too many candidates for a lock-step scan: the lane with the widest box goes to the fallback kernel, which searches one
+          // query with all 32 lanes; after a few of those the whole group goes
+          const float myR = act_g ? (h0 - l0) : -1.0f;
+          const float maxR = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fmaxf(myR, 0.f))));
+          const bool all_go = attempt >= 3;
+          if (act_g && (all_go || myR == maxR)) { kicked = true; act_g = false; }
+          if (!__any_sync(FULL, act_g)) { total = 0; break; }
         }
-        if (lane < ncx * ncy * ncz) {
-          const unsigned cx = (ix0 >> sh) + (unsigned)(lane % ncx), cy = (iy0 >> sh) + (unsigned)((lane / ncx) % ncy), cz = (iz0 >> sh) + (unsigned)(lane / (ncx * ncy));
-          const unsigned long long pre = morton3(cx, cy, cz);
-          lo = lower_bound_bucketed(codes, bucket_start, pre << (3 * sh));
-          const int hi = (sh >= MORTON_BITS) ? n : lower_bound_bucketed(codes, bucket_start, (pre + 1ull) << (3 * sh));
-          cnt = hi - lo;
-        }
-      }
-      incl = cnt;
-      #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
-      total = __shfl_sync(FULL, incl, 31);
-      excl = incl - cnt;
-      if (total <= KNN_RAW_CAP) break;
-      // too many candidates for a lock-step scan: the lane with the widest box goes to the fallback kernel, which searches one
-      // query with all 32 lanes; after a few of those the whole group goes
-      const float myR = act_g ? (h0 - l0) : -1.0f;
-      const float maxR = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(fmaxf(myR, 0.f))));
-      const bool all_go = attempt >= 3;
-      if (act_g && (all_go || myR == maxR)) { kicked = true; act_g = false; }
-      if (!__any_sync(FULL, act_g)) { total = 0; break; }
-    }
-    st_raw += total;
-    const bool act2 = act_g;
+        st_raw += total;
 
-    // ---- c. stage the candidates of the ranges (clipped against the box, the window left out) and scan them tile by tile
-    int ns = 0;
-    #pragma unroll 1
-    for (int base = 0; base < total; base += 32) {
-      const int g = base + lane;
-      int o = 0, b = 31;                                     // owning cell: the first lane whose inclusive count exceeds g
-      #pragma unroll
-      for (int s = 0; s < 5; s++) {
-        const int mid = (o + b) >> 1;
-        const int v = __shfl_sync(FULL, incl, mid);
-        if (v <= g) o = mid + 1; else b = mid;
-      }
-      const int cell_lo = __shfl_sync(FULL, lo, o), cell_ex = __shfl_sync(FULL, excl, o);
-      bool keep = false;
-      float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (g < total) {
-        const int pos = cell_lo + (g - cell_ex);
-        c = __ldg(sorted + pos);
-        keep = c.x >= lox && c.x <= hix && c.y >= loy && c.y <= hiy && c.z >= loz && c.z <= hiz && (unsigned)(pos - wlo) >= (unsigned)wcnt;
-        c.w = __int_as_float(pos);
-      }
-      const unsigned km = __ballot_sync(FULL, keep);
-      if (keep) stage[ns + __popc(km & ((1u << lane) - 1u))] = c;
-      ns += __popc(km);
-      if (ns > KNN_STAGE - 32 || base + 32 >= total) {
-        if ((ns & 1) && lane == 0) stage[ns] = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, 0.f);
-        __syncwarp();
-        st_staged += ns;
-        knn_scan_tile<KC>(L, act2, q, stage, (ns + 1) & ~1, sorted, plist, pend, st_events);
-        ns = 0;
-        __syncwarp();
+        // ---- stage the candidates of the ranges (clipped against the box, the window left out) and scan them tile by tile.
+        //      Two candidates per lane and step: two independent loads in flight
+        int ns = 0;
+        #pragma unroll 1
+        for (int base = 0; base < total; base += 64) {
+          float4 c[2];
+          bool keep[2];
+          #pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int g = base + h * 32 + lane;
+            int o = 0, b = 31;                               // owning cell: the first lane whose inclusive count exceeds g
+            #pragma unroll
+            for (int s = 0; s < 5; s++) {
+              const int mid = (o + b) >> 1;
+              const int v = __shfl_sync(FULL, incl, mid);
+              if (v <= g) o = mid + 1; else b = mid;
+            }
+            const int cell_lo = __shfl_sync(FULL, lo, o), cell_ex = __shfl_sync(FULL, excl, o);
+            const int pos = cell_lo + (g - cell_ex);
+            c[h] = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, 0.f);
+            if (g < total) c[h] = __ldg(sorted + pos);
+            keep[h] = c[h].x >= lox && c[h].x <= hix && c[h].y >= loy && c[h].y <= hiy && c[h].z >= loz && c[h].z <= hiz &&
+                      (unsigned)(pos - wlo) >= (unsigned)wcnt;   // false for the NaN filler
+            c[h].w = __int_as_float(pos);
+          }
+          #pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const unsigned km = __ballot_sync(FULL, keep[h]);
+            if (keep[h]) stage[ns + __popc(km & ((1u << lane) - 1u))] = c[h];
+            ns += __popc(km);
+          }
+          if (ns > KNN_STAGE - 64 || base + 64 >= total) {
+            if (lane < 3) stage[ns + lane] = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, 0.f);   // pad to a multiple of 4
+            __syncwarp();
+            st_staged += ns;
+            #pragma unroll 1
+            for (int s = 0; s < ns; s += 4) {
+              float cur = a[KC - 1];                        // == thr unless a list ran full (below)
+              float4 p[4];
+              float d[4];
+              #pragma unroll
+              for (int h = 0; h < 4; h++) p[h] = stage[s + h];   // broadcast reads
+              #pragma unroll
+              for (int h = 0; h < 4; h++) d[h] = dist2_exact(q, p[h]);
+              const float dmin = fminf(fminf(d[0], d[1]), fminf(d[2], d[3]));   // NaN-safe: fminf drops the NaN filler
+              if (__any_sync(FULL, act_g && dmin <= cur)) {
+                st_events++;
+                #pragma unroll
+                for (int h = 0; h < 4; h++) {
+                  if (act_g && d[h] <= cur) {
+                    if (npass < KNN_PL) { pl_pos[npass * 32] = __float_as_int(p[h].w); pl_d[npass * 32] = d[h]; npass++; } else overflow = true;
+                  }
+                }
+                // a list that is nearly full is brought up to date by single insertions and stripped of what fell behind; rare
+                if (__any_sync(FULL, npass > KNN_PL - 4)) {
+                  const int mx = __reduce_max_sync(FULL, npass - nmerged);
+                  #pragma unroll 1
+                  for (int e = 0; e < mx; e++) chain_insert<KC>(a, nmerged + e < npass ? pl_d[(nmerged + e) * 32] : INF);
+                  const float lim = a[KC - 1];
+                  int m2 = 0;
+                  #pragma unroll 1
+                  for (int e = 0; e < npass; e++) {
+                    const float dd = pl_d[e * 32];
+                    if (dd <= lim) { pl_pos[m2 * 32] = pl_pos[e * 32]; pl_d[m2 * 32] = dd; m2++; }
+                  }
+                  npass = m2; nmerged = m2;
+                  if (npass > KNN_PL - 4) overflow = true;  // that many candidates tie inside the k-th distance
+                }
+              }
+            }
+            ns = 0;
+            __syncwarp();
+          }
+        }
       }
     }
+
+    // ---- list update: sort up to KC pending distances (comparator network on registers), keep the KC smallest of the two sorted lists
+    //      (min(a[i], x[KC-1-i]) is that set) and sort again; repeated while a lane has distances pending
+    #pragma unroll 1
+    for (;;) {
+      const int pending = npass - nmerged;
+      if (!__any_sync(FULL, pending > 0)) break;
+      float x[KC];
+      #pragma unroll
+      for (int i = 0; i < KC; i++) x[i] = i < pending ? pl_d[(nmerged + i) * 32] : INF;
+      nmerged += min(pending, KC);
+      #pragma unroll 1
+      for (int pass = 0; pass < 2; pass++) {
+        sort_network<KC>(x);
+        if (pass == 0) {
+          #pragma unroll
+          for (int i = 0; i < KC / 2; i++) { const float u = x[i], v = x[KC - 1 - i]; x[i] = fminf(a[i], v); x[KC - 1 - i] = fminf(a[KC - 1 - i], u); }
+          if (KC & 1) x[KC / 2] = fminf(a[KC / 2], x[KC / 2]);
+        }
+      }
+      #pragma unroll
+      for (int i = 0; i < KC; i++) a[i] = x[i];
+    }
+    if (phase < 3) { npass = 0; nmerged = 0; }              // window entries are tracked by wmask, not by the list
   }
   if (stats) {
     if (lane == 0) {
       atomicAdd(stats + 0, (unsigned long long)st_raw); atomicAdd(stats + 1, (unsigned long long)st_staged); atomicAdd(stats + 2, (unsigned long long)st_events);
       atomicAdd(stats + 3, (unsigned long long)st_groups); atomicAdd(stats + 6, 1ull); atomicMax(stats + 5, (unsigned long long)st_raw);
     }
-    atomicAdd(stats + 4, (unsigned long long)L.npass);
+    atomicAdd(stats + 4, (unsigned long long)npass);
   }
 
-  // ---- d. the neighbour set: everything below tau*, then the smallest original indices among the ties at tau*
-  const float tau = L.a[KC - 1];
-  const int npass = min(L.npass, KNN_PL);
+  // ---- the neighbour set: everything below tau*, then the smallest original indices among the ties at tau*; the candidates are the
+  //      window entries flagged in `wmask` and the list (whose distances are stored). The selected positions overwrite the list from
+  //      the front (m never runs ahead of the read position; the window part is capped at the k-1 entries that can be below tau*)
+  const float tau = a[KC - 1];
   int m = 0, nt = 0;
+  // 1. list entries first, compacted in place
+  {
+    int mm = 0;
+    #pragma unroll 1
+    for (int e = 0; e < npass; e++) {
+      const float d = pl_d[e * 32];
+      const int pos = pl_pos[e * 32];
+      if (d < tau) { pl_pos[mm * 32] = pos; mm++; }
+      else if (d == tau) { if (nt < KNN_TIE) tie[nt * 32] = pos; nt++; }
+    }
+    m = mm;
+  }
+  // 2. window entries appended behind them: at most k - 1 entries in all; the position half and the distance half of the list are
+  //    contiguous, so the selection may use both (2 * KNN_PL >= 32 slots)
   #pragma unroll 1
-  for (int e = 0; e < npass; e++) {
-    const int pos = plist[e * 32];
-    const float d = dist2_exact(q, __ldg(sorted + pos));
-    if (d < tau) { plist[m * 32] = pos; m++; }
-    else if (d == tau) { if (nt < KNN_TIE) tie[nt * 32] = pos; nt++; }
+  while (wmask) {
+    const int w = __ffsll((long long)wmask) - 1;
+    wmask &= wmask - 1;
+    const float d = dist2_exact(q, __ldg(sorted + wlo + w));
+    if (d < tau) { if (m < 2 * KNN_PL) pl_pos[m * 32] = wlo + w; m++; }      // past KNN_PL the entries run on into the (now dead) distance half
+    else if (d == tau) { if (nt < KNN_TIE) tie[nt * 32] = wlo + w; nt++; }
   }
   const int need = k - m;
-  bool ok = finite && !kicked && !L.overflow && L.npass <= KNN_PL && need >= 1 && nt >= need && nt <= KNN_TIE;
+  bool ok = finite && !kicked && !overflow && need >= 1 && nt >= need && nt <= KNN_TIE;
   if (ok) {
     if (nt == need) {
-      for (int u = 0; u < nt; u++) plist[(m + u) * 32] = tie[u * 32];
+      for (int u = 0; u < nt; u++) pl_pos[(m + u) * 32] = tie[u * 32];
     } else {
       int prev = -1;
       for (int u = 0; u < need; u++) {
@@ -520,23 +574,23 @@ knn_chunk_kernel(const KnnCloud* __restrict__ clouds, int n_clouds, int total_ch
           const int oi = __float_as_int(__ldg(sorted + pos).w);
           if (oi > prev && oi < best) { best = oi; best_pos = pos; }
         }
-        plist[(m + u) * 32] = best_pos; prev = best;
+        pl_pos[(m + u) * 32] = best_pos; prev = best;
       }
     }
   }
 
-  // ---- e. covariance of the k neighbours (rot_vgicp_impl.hpp:446-456) + regulariser (:458-492)
+  // ---- covariance of the k neighbours (rot_vgicp_impl.hpp:446-456) + regulariser (:458-492)
   if (in_cloud) {
     const int self = __float_as_int(q.w);
     if (ok) {
       double sx = 0, sy = 0, sz = 0;
-      #pragma unroll 1
-      for (int u = 0; u < k; u++) { const float4 p = __ldg(sorted + plist[u * 32]); sx += (double)p.x; sy += (double)p.y; sz += (double)p.z; }
+      #pragma unroll 4
+      for (int u = 0; u < k; u++) { const float4 p = __ldg(sorted + pl_pos[u * 32]); sx += (double)p.x; sy += (double)p.y; sz += (double)p.z; }
       const double mx = sx / k, my = sy / k, mz = sz / k;
       double cc[6] = {0, 0, 0, 0, 0, 0};
-      #pragma unroll 1
+      #pragma unroll 4
       for (int u = 0; u < k; u++) {
-        const float4 p = __ldg(sorted + plist[u * 32]);
+        const float4 p = __ldg(sorted + pl_pos[u * 32]);
         const double dx = (double)p.x - mx, dy = (double)p.y - my, dz = (double)p.z - mz;
         cc[0] += dx * dx; cc[1] += dx * dy; cc[2] += dx * dz; cc[3] += dy * dy; cc[4] += dy * dz; cc[5] += dz * dz;
         if (C.knn_out) C.knn_out[(size_t)self * k + u] = __float_as_int(p.w);
@@ -976,7 +1030,7 @@ static cudaError_t launch_chunk(const KnnGroup& g, int total_chunks, cudaStream_
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = std::max(1, std::min(2 * sms, (total_chunks + KNN_WARPS - 1) / KNN_WARPS));   // 2 resident CTAs per SM
+  const int grid = std::max(1, std::min(3 * sms, (total_chunks + KNN_WARPS - 1) / KNN_WARPS));   // 3 resident CTAs per SM
   knn_chunk_kernel<KC><<<grid, KNN_WARPS * 32, KNN_SMEM, stream>>>(g.s.clouds, g.n_clouds, total_chunks, g.s.sorted, g.s.codes_a, g.s.bucket_start, g.s.bbox,
                                                                     g.s.fail, g.k, g.method, g.stats);
   return cudaGetLastError();
