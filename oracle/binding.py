@@ -402,6 +402,7 @@ class SCManager:
 
 
 _REF_SC_PATH = os.path.join(_HERE, "_ref", "librolo_ref_sc.so")
+_REF_FE_PATH = os.path.join(_HERE, "_ref", "librolo_ref_fe.so")
 
 
 def ref_sc_available() -> bool:
@@ -567,3 +568,72 @@ class Reference:
 
     def getFinalHessian(self):
         H = np.empty((6, 6)); self.L.rr_get_final_hessian(self.h, _d(H)); return H
+
+# ---- the reference's own range-image node sources (oracle/ref_fe_driver.cpp: src/imageProjection.cpp + src/featureExtraction.cpp compiled
+# from /root/reference against oracle/ref_shim_ros): same call surface and result dictionaries as image_projection / feature_extraction
+def ref_fe_available() -> bool:
+    return os.path.exists(_REF_FE_PATH)
+
+
+_ref_fe = {}
+
+
+def _ref_fe_lib(horizon: int = 0):
+    """projectPointCloud keeps `static float ang_res_x = 360.0 / float(Horizon_SCAN)` (imageProjection.cpp:439): initialised by the
+    first call and never again, because a node runs with one Horizon_SCAN for its lifetime. A test process that projects frames of
+    several widths therefore loads one private copy of the library per width (a copied file is a distinct shared object with its
+    own statics)."""
+    if horizon not in _ref_fe:
+        import shutil, tempfile
+        path = _REF_FE_PATH
+        if _ref_fe:
+            fd, path = tempfile.mkstemp(prefix=f"librolo_ref_fe_{horizon}_", suffix=".so"); os.close(fd)
+            shutil.copyfile(_REF_FE_PATH, path)
+        _ref_fe[horizon] = C.CDLL(path)
+    return _ref_fe[horizon]
+
+
+def ref_image_projection(raw: np.ndarray, n_scan, horizon, downsample_rate=1, min_range=2.0, max_range=1000.0, ring_offset=20, deskew=None):
+    L = _ref_fe_lib(horizon)
+    raw = np.ascontiguousarray(raw)
+    cells = n_scan * horizon
+    rim = np.empty((n_scan, horizon), dtype=np.float32)
+    ext = np.empty((cells, 4), dtype=np.float32); col = np.empty(cells, dtype=np.int32); rng = np.empty(cells, dtype=np.float32)
+    st = np.empty(n_scan, dtype=np.int32); en = np.empty(n_scan, dtype=np.int32)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    inc = np.ascontiguousarray(deskew["incre_rpy"] if deskew else (0, 0, 0), dtype=np.float32)
+    n = L.rfe_image_projection(vp(raw), C.c_size_t(raw.shape[0]), C.c_int(raw.dtype.itemsize), C.c_int(ring_offset), C.c_int(n_scan), C.c_int(horizon),
+                               C.c_int(downsample_rate), C.c_float(min_range), C.c_float(max_range), C.c_int(1 if deskew else 0),
+                               C.c_int(deskew["time_offset"] if deskew else 0), vp(inc), C.c_float(deskew["scan_period"] if deskew else 0.1),
+                               C.c_double(deskew["odom_time_diff"] if deskew else -1.0), vp(rim), vp(ext), vp(col), vp(rng), vp(st), vp(en))
+    return {"range_image": rim, "extracted": ext[:n].copy(), "point_col_ind": col[:n].copy(), "point_range": rng[:n].copy(),
+            "start_ring_index": st, "end_ring_index": en, "n": n}
+
+
+def ref_feature_extraction(proj: dict, n_scan, horizon, edge_threshold=0.8, surf_threshold=0.1, surf_leaf_size=0.4):
+    L = _ref_fe_lib(horizon)
+    n = proj["n"]
+    ext = np.ascontiguousarray(proj["extracted"], dtype=np.float32); col = np.ascontiguousarray(proj["point_col_ind"], dtype=np.int32)
+    rng = np.ascontiguousarray(proj["point_range"], dtype=np.float32)
+    st = np.ascontiguousarray(proj["start_ring_index"], dtype=np.int32); en = np.ascontiguousarray(proj["end_ring_index"], dtype=np.int32)
+    curv = np.empty(n, dtype=np.float32); picked = np.empty(n, dtype=np.int32); label = np.empty(n, dtype=np.int32)
+    corner = np.empty((n_scan * 120, 4), dtype=np.float32); surf = np.empty((n_scan * horizon, 4), dtype=np.float32)
+    nc = C.c_int(); ns = C.c_int()
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    L.rfe_feature_extraction(vp(ext), vp(col), vp(rng), vp(st), vp(en), C.c_int(n), C.c_int(n_scan), C.c_int(horizon), C.c_float(edge_threshold),
+                             C.c_float(surf_threshold), C.c_float(surf_leaf_size), vp(curv), vp(picked), vp(label), vp(corner), C.byref(nc), vp(surf), C.byref(ns))
+    return {"curvature": curv, "neighbor_picked": picked, "label": label, "corner": corner[:nc.value].copy(), "surface": surf[:ns.value].copy()}
+
+def require_ref(available, what: str):
+    """Module-level guard of the tests that pin the oracle to oracle/_ref: where the reference checkout exists the library is built
+    on demand and its absence is an ERROR (a silently skipped pin is no pin); elsewhere (the GPU box, where the prebuilt files
+    travel with the tree) a missing library skips the module."""
+    import pytest
+    if available():
+        return
+    if os.path.isdir("/root/reference/include/rot_gicp"):
+        build_ref()
+        if not available():
+            raise RuntimeError(f"{what} missing although /root/reference exists: `make -C oracle ref` failed")
+        return
+    pytest.skip(f"{what} not built and no reference checkout on this machine", allow_module_level=True)

@@ -9,7 +9,12 @@
 // floor(p * inverse_leaf) - min_b in float, centroid of all fields per leaf, output in ascending
 // leaf-index order.
 //
-// PARITY UNPINNED BY THE REFERENCE: no golden data exists for these passes.
+// PINNED against the reference's own code: no golden data exists for these passes, but the two node sources compile
+// from where they lie into oracle/_ref/librolo_ref_fe.so (oracle/ref_fe_driver.cpp against oracle/ref_shim_ros), and
+// tests/test_frontend_vs_ref_cpu.py requires this restatement to equal them: range image, compaction, index arrays, curvature,
+// marks, labels and corner clouds exactly (labels / marks up to the sort ties of Q7), deskewed coordinates to one float ulp
+// (glibc sinf / cosf vs correctly rounded), surface centroids to 1e-6 (summation order inside a leaf). What stays third-party
+// and restated on both sides: pcl::VoxelGrid, pcl::getTransformation.
 // Single-frame, stateless restatement. Reference quirks handled explicitly:
 //  Q7  std::sort tie order is unspecified -> ties broken by point index here (and on the GPU).
 //  Q8  the reference's work arrays are `new`-allocated once and never cleared: entries outside

@@ -1,0 +1,1 @@
+// unused by the member functions under test: empty stand-in (test infrastructure only)

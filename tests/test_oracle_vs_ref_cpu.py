@@ -1,14 +1,15 @@
 """CPU: the oracle restatement against oracle/_ref — the REFERENCE's own rot_gicp sources compiled from
 /root/reference/include (nothing copied) with oracle/ref_shim standing in for Eigen/PCL/Boost (absent from the image).
 This is what pins the restatement of rot_vgicp_impl.hpp / lsq_registration_impl.hpp / vmp_voxel.hpp / so3.hpp line by
-line. Skipped where oracle/_ref/librolo_ref.so has not been built (it cannot be built without /root/reference)."""
+line. Where /root/reference exists the library is built on demand and its absence is an error; only a machine without the checkout
+and without the prebuilt file skips."""
 import numpy as np
 import pytest
 
 from oracle import binding as ob
 from rolo_b200 import synth
 
-pytestmark = pytest.mark.skipif(not ob.ref_available(), reason="oracle/_ref not built (needs /root/reference)")
+ob.require_ref(ob.ref_available, "oracle/_ref/librolo_ref.so")
 
 
 def _pair(cls, tgt, src, uniform=None, method=ob.DIRECT1, reg=ob.REG_PLANE):

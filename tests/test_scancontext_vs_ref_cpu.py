@@ -7,7 +7,7 @@ import pytest
 from oracle import binding as ob
 from rolo_b200 import synth
 
-pytestmark = pytest.mark.skipif(not ob.ref_sc_available(), reason="oracle/_ref/librolo_ref_sc.so not built (needs /root/reference)")
+ob.require_ref(ob.ref_sc_available, "oracle/_ref/librolo_ref_sc.so")
 
 
 def test_oracle_equals_the_reference_scancontext():
