@@ -159,8 +159,9 @@ int rg_set_profile(rg_ctx*, int on);
 int  rg_batch_create(int device, int n_pairs, rg_batch** out);
 void rg_batch_destroy(rg_batch*);
 rg_ctx* rg_batch_ctx(rg_batch*, int pair);      /* per-pair context for setters / inputs / results  */
-/* align() of every pair in lock step: per stage ONE launch covers all pairs
- * (covariances, voxel maps, then one fused linearize launch per GN/LM evaluation).              */
+/* align() of every pair in lock step: the covariances are estimated in groups of 32 pairs per launch chain (one radix sort, one
+ * kNN + covariance launch per group), every voxel map by one launch chain, then one fused linearize launch per GN/LM evaluation
+ * covers all pairs.                                                                              */
 int  rg_batch_align(rg_batch*, const float* guesses /* n_pairs*16 or NULL */, float* final_transformations /* n_pairs*16 */);
 double rg_batch_last_linearize_us(const rg_batch*);   /* mean device time of the fused launches (CUDA events) */
 int    rg_batch_last_linearize_launches(const rg_batch*);
@@ -189,6 +190,43 @@ int rg_set_source_shard(rg_ctx*, size_t lo, size_t hi);
  * optimiser decisions). world <= 8. A peer that never arrives is reported as RG_ERR_CUDA after a bounded wait. */
 int rg_shard_export(rg_ctx*, void* ipc_handle_64_bytes);
 int rg_shard_connect(rg_ctx*, int rank, int world, const void* ipc_handles /* world x 64 bytes */);
+/* Target-sharded SETUP of such a registration ("target is sharded, partial accumulators built locally and merged once per
+ * align"). After rg_set_target_shard(rank, world) this rank estimates the covariances of ONE share of the target only (the target's
+ * Morton order is dealt out in blocks of 2048 points, round-robin over the ranks — the expensive queries cluster in space, contiguous
+ * slices would be badly balanced; the spatial index still covers the whole cloud, so the neighbourhoods are un-cut) and accumulates only those points into its voxel sums (vmp_voxel.hpp:167-197 up to, not including,
+ * finalize). Once per voxel-map build the merge hook receives the rank's compact voxel list — device pointers keys uint64[n_local]
+ * (packed voxel key) and sums double[n_local * 10] (sum of points xyz, sum of covariances xx xy xz yy yz zz, point count) — gathers the
+ * lists of all ranks by whatever transport it likes (NCCL all-gather in rolo_b200/dist.py) and hands the concatenation to
+ * rg_voxel_import, which adds entries with equal keys and finalizes (vmp_voxel.hpp:102-107). world <= 1 restores the full setup.
+ * The target covariances must be computed by the context (rg_calculate_covariances / rg_align), not installed from outside. */
+typedef int (*rg_voxel_merge_fn)(void* user, const void* keys_dev, const void* sums_dev, int n_local, void* stream);
+int rg_set_target_shard(rg_ctx*, int rank, int world);
+int rg_set_voxel_merge_hook(rg_ctx*, rg_voxel_merge_fn fn, void* user);
+int rg_voxel_import(rg_ctx*, const void* keys_dev, const void* sums_dev, int n_total);
+
+/* voxelmap_.reset() (rot_vgicp_impl.hpp:147): the next linearize rebuilds the voxel map from the target and its covariances */
+int rg_reset_voxelmap(rg_ctx*);
+
+/* ---- the optimiser alone ----------------------------------------------------------------------------------
+ * LsqRegistration's Gauss-Newton / LM / SO3-LM / translation-LM step logic (lsq_registration_impl.hpp:55-335: LDLT solves, damping,
+ * rho test, convergence) as a resumable request / feed state machine. rg_align drives it internally; the C++ base class
+ * fast_gicp::LsqRegistration (include/rot_gicp/gicp/lsq_registration.hpp) drives it through the reference's protected virtuals
+ * (linearize / so3_linearize / compute_error / t3_linearize / compute_t_error), so user subclasses keep working:
+ *   rg_lsq_begin_align(q, guess) or rg_lsq_begin_translation(q, trans);
+ *   while ((kind = rg_lsq_want(q, pose, t3)) != RG_REQ_NONE) { evaluate the request; rg_lsq_feed(q, H, b, cost); }
+ *   rg_lsq_state(q, ...).
+ * H / b are row-major 6x6 / 6 (RG_REQ_LIN6, RG_REQ_T3_LIN) or 3x3 / 3 (RG_REQ_LIN3) and NULL for the two error requests. */
+typedef struct rg_lsq rg_lsq;
+enum { RG_REQ_NONE = 0, RG_REQ_LIN6, RG_REQ_LIN3, RG_REQ_ERROR, RG_REQ_T3_LIN, RG_REQ_T_ERROR };
+rg_lsq* rg_lsq_create(void);
+void rg_lsq_destroy(rg_lsq*);
+void rg_lsq_configure(rg_lsq*, int optimizer, int max_iterations, double rotation_epsilon, double transformation_epsilon,
+                      double lm_init_lambda_factor, int debug_print);
+void rg_lsq_begin_align(rg_lsq*, const double guess[16]);
+void rg_lsq_begin_translation(rg_lsq*, const double trans[3]);
+int  rg_lsq_want(rg_lsq*, double pose16[16], double t3[3]);
+void rg_lsq_feed(rg_lsq*, const double* H, const double* b, double cost);
+void rg_lsq_state(const rg_lsq*, double pose16[16], double t3[3], int* nr_iterations, int* converged, int* failed, double final_hessian36[36]);
 
 /* ---- upstream range-image passes ------------------------------------------------------------------------ */
 /* ImageProjection::projectPointCloud + cloudExtraction (imageProjection.cpp:399-505); deskew off unless rg_set_deskew was called

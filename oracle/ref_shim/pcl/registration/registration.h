@@ -26,6 +26,8 @@ template <typename PointSource, typename PointTarget, typename Scalar = float> c
   bool hasConverged() const { return converged_; }
   void setMaximumIterations(int n) { max_iterations_ = n; }
   void setTransformationEpsilon(double e) { transformation_epsilon_ = e; }
+  using KdTreePtr = std::shared_ptr<pcl::search::KdTree<PointTarget>>;
+  void setSearchMethodTarget(const KdTreePtr& tree, bool force_no_recompute = false) { tree_ = tree; force_no_recompute_ = force_no_recompute; }
   void align(PointCloudSource& output) { align(output, Matrix4::Identity()); }
   void align(PointCloudSource& output, const Matrix4& guess) {
     output = *input_;
@@ -42,6 +44,8 @@ template <typename PointSource, typename PointTarget, typename Scalar = float> c
   Matrix4 final_transformation_;
   double transformation_epsilon_ = 0.0;
   bool converged_ = false;
+  KdTreePtr tree_;
+  bool force_no_recompute_ = false;
 };
 }  // namespace pcl
 #endif

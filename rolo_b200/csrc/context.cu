@@ -118,7 +118,7 @@ int upload_cloud(rg_ctx* c, Cloud& cl, const float* host, size_t n, size_t strid
   const int n_pad = (int)((n + TILE_PTS - 1) / TILE_PTS * TILE_PTS);
   RG_CUDA(c, cl.pts.ensure(c->device, std::max(n_pad, TILE_PTS)));
   RG_CUDA(c, cl.cov6.ensure(c->device, (size_t)std::max(n_pad, TILE_PTS) * COV_PLANES));
-  cl.n = (int)n; cl.n_pad = n_pad; cl.has_cov = false; cl.host_identity = host;
+  cl.n = (int)n; cl.n_pad = n_pad; cl.has_cov = false; cl.host_identity = host; cl.shard_rank = 0; cl.shard_world = 1; cl.sorted_view = nullptr;
   if (n == 0) return RG_OK;
   cudaStream_t us = c->upload_stream ? c->upload_stream : c->stream;
   if (us != c->stream) {   // order after whatever the context queued before (e.g. the previous frame still using these buffers)
@@ -149,7 +149,7 @@ int upload_cloud_device(rg_ctx* c, Cloud& cl, const float* dev, size_t n, cudaSt
   const int n_pad = (int)((n + TILE_PTS - 1) / TILE_PTS * TILE_PTS);
   RG_CUDA(c, cl.pts.ensure(c->device, std::max(n_pad, TILE_PTS)));
   RG_CUDA(c, cl.cov6.ensure(c->device, (size_t)std::max(n_pad, TILE_PTS) * COV_PLANES));
-  cl.n = (int)n; cl.n_pad = n_pad; cl.has_cov = false; cl.host_identity = dev;
+  cl.n = (int)n; cl.n_pad = n_pad; cl.has_cov = false; cl.host_identity = dev; cl.shard_rank = 0; cl.shard_world = 1; cl.sorted_view = nullptr;
   if (n == 0) return RG_OK;
   if (user_stream && user_stream != c->stream) {   // order after the producer stream
     cudaEvent_t ev;
@@ -205,12 +205,15 @@ int calc_cov_group(rg_ctx* c, const std::vector<Cloud*>& clouds, KnnBufs& bufs, 
     return RG_OK;
   }
   RG_CUDA(c, bufs.ensure(c->device, total, (int)clouds.size()));
+  if (&bufs == &c->knn) { c->src.sorted_view = nullptr; c->tgt.sorted_view = nullptr; }   // the Morton-ordered copies in this scratch are about to be overwritten
   std::vector<KnnCloud> desc(clouds.size());
   int off = 0, chunk_off = 0;
   for (size_t i = 0; i < clouds.size(); i++) {
     desc[i].pts = clouds[i]->pts.p; desc[i].cov6 = clouds[i]->cov6.p; desc[i].knn_out = (knn_out && clouds.size() == 1) ? knn_out : nullptr;
     desc[i].n = clouds[i]->n; desc[i].off = off; desc[i].chunk_off = chunk_off;
-    off += clouds[i]->n; chunk_off += (clouds[i]->n + 31) / 32;
+    desc[i].shard_rank = clouds[i]->shard_rank; desc[i].shard_world = clouds[i]->shard_world;
+    clouds[i]->sorted_view = bufs.sorted.p + off;
+    off += clouds[i]->n; chunk_off += knn_owned_chunks(clouds[i]->n, clouds[i]->shard_rank, clouds[i]->shard_world);
   }
   KnnGroup g;
   g.clouds = desc.data(); g.n_clouds = (int)desc.size(); g.total = (int)total; g.max_n = max_n; g.k = k; g.method = c->regularization_method;
@@ -233,8 +236,16 @@ int calc_cov_group(rg_ctx* c, const std::vector<Cloud*>& clouds, KnnBufs& bufs, 
   return RG_OK;
 }
 
+// the share of the target this rank owns in a target-sharded registration
+void apply_target_shard(rg_ctx* c) {
+  Cloud& t = c->tgt;
+  if (c->tgt_world > 1 && !c->batch) { t.shard_rank = c->tgt_rank; t.shard_world = c->tgt_world; }
+  else { t.shard_rank = 0; t.shard_world = 1; }
+}
+
 int calc_cov(rg_ctx* c, Cloud& cl) {
   if (use_device(c)) return RG_ERR_CUDA;
+  if (&cl == &c->tgt) apply_target_shard(c);
   std::vector<Cloud*> one{&cl};
   return calc_cov_group(c, one, c->knn, c->stream);
 }
@@ -276,6 +287,31 @@ int build_voxelmap(rg_ctx* c) {
   if (use_device(c)) return RG_ERR_CUDA;
   VoxelBuild b;
   if (int rc = prepare_voxel_build(c, b)) return rc;
+  if (c->tgt_world > 1 && !c->batch) {
+    // target-sharded setup: accumulate this rank's slice, hand the compact voxel list to the merge hook, which gathers the lists
+    // of all ranks and calls rg_voxel_import (the finalize pass runs there)
+    if (!c->voxel_merge_fn) return set_err(c, RG_ERR_INVALID, "target-sharded registration without a voxel merge hook (rg_set_voxel_merge_hook)");
+    if (!c->tgt.sorted_view) {   // covariances installed from outside, or the scratch was reused since: estimate this rank's slice again
+      c->tgt.has_cov = false;
+      if (int rc = calc_cov(c, c->tgt)) return rc;
+      if (int rc = prepare_voxel_build(c, b)) return rc;
+    }
+    b.order = c->tgt.sorted_view; b.shard_rank = c->tgt.shard_rank; b.shard_world = c->tgt.shard_world;
+    RG_CUDA(c, launch_voxel_build(b, c->stream, false));
+    g_launches += 3;
+    int h[2] = {0, 0};
+    RG_CUDA(c, cudaMemcpyAsync(h, c->counters.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    RG_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (h[1] != 0) return set_err(c, RG_ERR_INVALID, "voxel coordinate out of the +-2^20 key range (or table overflow)");
+    RG_CUDA(c, c->vox_keys.ensure(c->device, std::max(h[0], 1)));
+    RG_CUDA(c, launch_voxel_keys(b, c->vox_keys.p, c->stream));
+    g_launches += 1;
+    c->voxel_ok = false;
+    if (int rc = c->voxel_merge_fn(c->voxel_merge_user, c->vox_keys.p, c->sums.p, h[0], (void*)c->stream))
+      return set_err(c, RG_ERR_CUDA, "voxel merge hook failed (" + std::to_string(rc) + ")");
+    if (!c->voxel_ok) return set_err(c, RG_ERR_INVALID, "voxel merge hook returned without calling rg_voxel_import");
+    return RG_OK;
+  }
   RG_CUDA(c, launch_voxel_build(b, c->stream));
   g_launches += 4;
   c->voxel_ok = true; c->n_vox = -1; c->st_ok = false; c->have_corr = false;
@@ -464,7 +500,7 @@ int ensure_covariances(rg_ctx* c) {
   if (use_device(c)) return RG_ERR_CUDA;
   std::vector<Cloud*> todo;
   if (!c->src.has_cov) todo.push_back(&c->src);
-  if (!c->tgt.has_cov) todo.push_back(&c->tgt);
+  if (!c->tgt.has_cov) { apply_target_shard(c); todo.push_back(&c->tgt); }
   return calc_cov_group(c, todo, c->knn, c->stream);
 }
 
@@ -534,7 +570,7 @@ void rg_destroy(rg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->src.release(); c->tgt.release();
   c->table.release(); c->vox.release(); c->sums.release(); c->slot_of_point.release(); c->counters.release();
-  c->codes_in.release(); c->codes_out.release(); c->idx_in.release(); c->idx_out.release(); c->bbox.release(); c->sorted.release(); c->cub_temp.release(); c->knn_idx.release(); c->bucket_start.release(); c->knn.release();
+  c->codes_in.release(); c->codes_out.release(); c->idx_in.release(); c->idx_out.release(); c->bbox.release(); c->sorted.release(); c->cub_temp.release(); c->knn_idx.release(); c->bucket_start.release(); c->knn.release(); c->vox_keys.release();
   c->fe_raw.release(); c->fe_owner.release(); c->fe_row_count.release(); c->fe_col.release(); c->fe_start.release(); c->fe_end.release();
   c->fe_counts.release(); c->fe_picked.release(); c->fe_label.release(); c->fe_corner_cnt.release(); c->fe_surf_cnt.release();
   c->fe_range_image.release(); c->fe_prange.release(); c->fe_curv.release(); c->fe_full.release(); c->fe_extracted.release();
@@ -666,6 +702,8 @@ int rg_calculate_covariances(rg_ctx* c, int which) {
   return rc;
 }
 
+int rg_reset_voxelmap(rg_ctx* c) { CHECK_CTX(c); c->voxel_ok = false; c->st_ok = false; c->have_corr = false; return RG_OK; }
+
 int rg_create_voxelmap(rg_ctx* c) {
   CHECK_CTX(c);
   if (!c->tgt.has_cov) { if (int rc = calc_cov(c, c->tgt)) return rc; }
@@ -711,11 +749,22 @@ int rg_align(rg_ctx* c, const float guess[16], float out_T[16]) {
   if (c->src.n == 0 || c->tgt.n == 0) return set_err(c, RG_ERR_INVALID, "align: source/target cloud not set");
   c->voxel_ok = false; c->st_ok = false; c->have_corr = false;      // voxelmap_.reset() (rot_vgicp_impl.hpp:147)
   if (int rc = check_grid(c)) return rc;
+  static const bool trace = std::getenv("ROLO_TRACE") != nullptr;   // development aid: stage wall times of every align on stderr
+  const auto t0 = std::chrono::steady_clock::now();
   if (int rc = ensure_covariances(c)) return rc;
+  if (trace) cudaStreamSynchronize(c->stream);
+  const auto t1 = std::chrono::steady_clock::now();
+  if (trace) { if (int rc = prepare_linearize(c)) return rc; cudaStreamSynchronize(c->stream); }
+  const auto t2 = std::chrono::steady_clock::now();
   double g[16];
   if (guess) for (int i = 0; i < 16; i++) g[i] = (double)guess[i]; else host::mat4_identity(g);
   c->lsq.begin_align(g);
   if (int rc = run_driver(c, nullptr, nullptr, 0, 0)) return rc;
+  if (trace) {
+    const auto t3 = std::chrono::steady_clock::now();
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    fprintf(stderr, "[rolo trace] align: covariances %.3f ms, voxel map + launch set-up %.3f ms, %d iterations %.3f ms\n", ms(t0, t1), ms(t1, t2), c->lsq.nr_iterations + 1, ms(t2, t3));
+  }
   if (fetch_voxel_count(c) < 0) return RG_ERR_INVALID;               // target voxel keys outside the +-2^20 cell range are an error, not dropped
   for (int i = 0; i < 16; i++) out_T[i] = (float)c->lsq.x0[i];      // final_transformation_ = x0.cast<float>() (lsq.hpp:177)
   return c->lsq.failed ? RG_ERR_NOT_CONVERGED : RG_OK;
@@ -901,6 +950,42 @@ int rg_shard_connect(rg_ctx* c, int rank, int world, const void* handles) {
   RG_CUDA(c, cudaDeviceSynchronize());
   c->p2p_rank = rank; c->p2p_world = world; c->shard_seq = 0; c->st_ok = false;
   c->reduce_fn = nullptr;
+  return RG_OK;
+}
+
+int rg_set_target_shard(rg_ctx* c, int rank, int world) {
+  CHECK_CTX(c);
+  if (world <= 1) { c->tgt_rank = 0; c->tgt_world = 0; }
+  else {
+    if (rank < 0 || rank >= world) return set_err(c, RG_ERR_INVALID, "rg_set_target_shard: rank out of range");
+    c->tgt_rank = rank; c->tgt_world = world;
+  }
+  c->tgt.has_cov = false; c->voxel_ok = false; c->st_ok = false; c->have_corr = false;
+  return RG_OK;
+}
+
+int rg_set_voxel_merge_hook(rg_ctx* c, rg_voxel_merge_fn fn, void* user) {
+  CHECK_CTX(c);
+  c->voxel_merge_fn = fn; c->voxel_merge_user = user;
+  return RG_OK;
+}
+
+int rg_voxel_import(rg_ctx* c, const void* keys_dev, const void* sums_dev, int n_total) {
+  CHECK_CTX(c);
+  if (use_device(c)) return RG_ERR_CUDA;
+  if (n_total < 0 || (n_total > 0 && (!keys_dev || !sums_dev))) return set_err(c, RG_ERR_INVALID, "rg_voxel_import: bad arguments");
+  if (n_total > c->tgt.n) return set_err(c, RG_ERR_INVALID, "rg_voxel_import: more voxel entries than target points");
+  VoxelBuild b;
+  if (int rc = prepare_voxel_build(c, b)) return rc;
+  const double* sums_in = (const double*)sums_dev;
+  if (n_total > 0 && sums_in >= c->sums.p && sums_in < c->sums.p + c->sums.cap) {   // the caller passed our own accumulator rows: they are rewritten below
+    RG_CUDA(c, c->staging.ensure(c->device, (size_t)n_total * 10 * sizeof(double)));
+    RG_CUDA(c, cudaMemcpyAsync(c->staging.p, sums_in, (size_t)n_total * 10 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    sums_in = (const double*)c->staging.p;
+  }
+  RG_CUDA(c, launch_voxel_import(b, (const unsigned long long*)keys_dev, sums_in, n_total, c->stream));
+  g_launches += 4;
+  c->voxel_ok = true; c->n_vox = -1; c->st_ok = false; c->have_corr = false;
   return RG_OK;
 }
 

@@ -161,7 +161,12 @@ struct Cloud {
   int n = 0, n_pad = 0;
   bool has_cov = false;
   const void* host_identity = nullptr;   // the reference compares cloud pointers (rot_vgicp_impl.hpp:113,134)
-  void clear() { n = 0; n_pad = 0; has_cov = false; host_identity = nullptr; }
+  // target-sharded registration: covariances exist only for the points this rank owns (blocks of the Morton order dealt round-robin,
+  // covariance.cuh: knn_owns); sorted_view = this cloud's Morton-ordered copy (xyz + original index) inside the covariance scratch,
+  // valid until that scratch is reused
+  int shard_rank = 0, shard_world = 1;
+  const float4* sorted_view = nullptr;
+  void clear() { n = 0; n_pad = 0; has_cov = false; host_identity = nullptr; shard_rank = 0; shard_world = 1; sorted_view = nullptr; }
   void release() { pts.release(); cov6.release(); clear(); }
 };
 
@@ -230,6 +235,9 @@ struct rg_ctx {
   double last_kernel_us = -1.0;
 
   rg_reduce_fn reduce_fn = nullptr; void* reduce_user = nullptr; int reduce_on_device = 0;
+  int tgt_rank = 0, tgt_world = 0;      // target-sharded setup (rg_set_target_shard): this rank's slice of the target's Morton order
+  rg_voxel_merge_fn voxel_merge_fn = nullptr; void* voxel_merge_user = nullptr;
+  DevBuf<unsigned long long> vox_keys;
   int shard_lo = 0, shard_hi = 0;       // evaluation range within the source cloud (0,0 = all)
   // fused NVLink reduction (rg_shard_connect)
   double* xchg = nullptr;               // own exchange buffer (plain cudaMalloc: exported through CUDA IPC)

@@ -296,7 +296,12 @@ knn_chunk_kernel(const KnnCloud* __restrict__ clouds, int n_clouds, int total_ch
   }
   const KnnCloud C = clouds[cloud];
   const int n = C.n;
-  const int j0 = (chunk - C.chunk_off) * 32;
+  int j0;
+  {
+    const int cl = chunk - C.chunk_off;                      // this cloud's cl-th owned chunk
+    if (C.shard_world > 1) { const int per = KNN_SHARD_BLOCK / 32; j0 = (((cl / per) * C.shard_world + C.shard_rank) * per + cl % per) * 32; }
+    else j0 = cl * 32;
+  }
   const float4* __restrict__ sorted = sorted_all + C.off;
   const unsigned long long* __restrict__ codes = codes_all + C.off;
   const int* __restrict__ bucket_start = bucket_all + (size_t)cloud * (N_BUCKETS + 1);
@@ -612,19 +617,58 @@ knn_chunk_kernel(const KnnCloud* __restrict__ clouds, int n_clouds, int total_ch
 }
 
 // ---------------------------------------------------------------------------------------------------
-// exact kNN of ONE query by a whole warp (k <= 32): the fallback behind the chunk kernel.
-//  * lanes 0..26 each locate one cell of the 3x3x3 block around the query at level L (two binary searches in parallel);
-//    a warp scan of the cell counts gives the candidate total, which also steers the level: too many candidates -> finer
-//    level, fewer than k -> coarser, before anything is scanned;
-//  * candidates are scanned 32 at a time (coalesced), the current top-32 lives one element per lane, sorted
-//    by (distance, index); a batch in which nobody beats the k-th distance costs one ballot; otherwise the
-//    winners are inserted by shuffle (few) or the batch is bitonic-sorted and merged (many);
-//  * the result is exact once the k-th distance is inside the radius the scanned block provably covers, else one level coarser.
+// exact kNN of ONE query by a whole warp (k <= 32): the fallback behind the chunk kernel, for the queries whose candidate region is too
+// large for a lock-step scan (a stray point next to a dense surface, a far return whose neighbours are metres away) or whose lists
+// overflowed (exact ties en masse).
+//  * the current top-32 lives one element per lane, sorted by (distance, index); candidates arrive 32 at a time (coalesced); a batch in
+//    which nobody beats the k-th key costs one ballot; otherwise the winners are inserted by shuffle (few) or the batch is
+//    bitonic-sorted and merged (many);
+//  * the 64 Morton-order neighbours of the query go first: their k-th distance bounds the search radius, so ONE pass over the cells
+//    that cover the ball's box (<= 32 cells of one level, one binary-search pair per lane) is exact — no level iteration, no restart.
 // Returns this lane's element of the ascending (distance, index) list (KEY_INF = none).
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void knn_warp_merge(unsigned long long& top, unsigned long long key, int k, bool first) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned long long kth = __shfl_sync(FULL, top, k - 1);
+  const bool pass = key < kth;
+  unsigned m = __ballot_sync(FULL, pass);
+  if (m == 0) return;
+  if (__popc(m) > 10) {
+    // bitonic sort of the batch (non-passing lanes carry +inf), then bitonic merge with the top-32
+    if (!pass) key = KEY_INF;
+    #pragma unroll
+    for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+      #pragma unroll
+      for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) bitonic_cmpx(key, j2, ((lane & k2) == 0) == ((lane & j2) == 0));
+    }
+    if (first) {
+      top = key;                                     // the top-32 is still empty: the sorted batch is the new top-32
+    } else {
+      const unsigned long long rev = __shfl_sync(FULL, key, 31 - lane);
+      if (rev < top) top = rev;
+      #pragma unroll
+      for (int j2 = 16; j2 > 0; j2 >>= 1) bitonic_cmpx(top, j2, (lane & j2) == 0);
+    }
+  } else {
+    while (m) {
+      const int srcl = __ffs(m) - 1;
+      m &= m - 1;
+      const unsigned long long ck = __shfl_sync(FULL, key, srcl);
+      const int pos = __popc(__ballot_sync(FULL, top < ck));      // elements that stay in front
+      const unsigned long long up = __shfl_up_sync(FULL, top, 1);
+      if (lane > pos) top = up; else if (lane == pos) top = ck;
+    }
+  }
+}
+
+// Level search: the 3x3x3 block of octree cells around the query is scanned at a level guessed from the Morton neighbours; the result is
+// exact once the k-th distance is inside the radius the block provably covers, else the block is taken one level coarser and scanned
+// again. Needs no a-priori bound: used when the Morton window gives a uselessly loose one.
+constexpr int KNN_BOX_CAP = 6144;     // fallback: box pass when the window bound's covering cells hold at most this many points, else the level search
 constexpr int KNN_CAND_CAP = 1024;    // prefer a finer level when the block holds more candidates than this
 
-__device__ unsigned long long knn_warp_query(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes,
+__device__ unsigned long long knn_warp_query_levels(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes,
                                              const int* __restrict__ bucket_start, int n, int k, const Quant& qn, int j, const float4 q) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -732,6 +776,84 @@ __device__ unsigned long long knn_warp_query(const float4* __restrict__ sorted, 
     if (kth != KEY_INF && (double)__uint_as_float((unsigned)(kth >> 32)) <= rs * rs * (1.0 - 1e-6)) break;
     no_finer = true;
     L--;
+  }
+  return top;
+}
+
+
+__device__ unsigned long long knn_warp_query(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes,
+                                             const int* __restrict__ bucket_start, int n, int k, const Quant& qn, int j, const float4 q) {
+  const unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  unsigned long long top = KEY_INF;                   // this lane's element of the sorted top-32
+  auto key_of = [&](const float4& p) {
+    const float d = dist2_exact(q, p);
+    return (d == d) ? (((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w)) : KEY_INF;
+  };
+  // the Morton window first
+  const int wcnt = min(KNN_WINDOW, n);
+  const int wlo = max(0, min(j - KNN_WINDOW / 2, n - wcnt));
+  #pragma unroll
+  for (int h = 0; h < KNN_WINDOW / 32; h++) {
+    const int w = h * 32 + lane;
+    unsigned long long key = KEY_INF;
+    if (w < wcnt) key = key_of(__ldg(sorted + wlo + w));
+    knn_warp_merge(top, key, k, h == 0);
+  }
+  const unsigned long long kthw = __shfl_sync(FULL, top, k - 1);
+  if (kthw == KEY_INF) return top;                    // fewer than k finite candidates in the window: only a non-finite query gets here
+  // the ball's box and its covering cells
+  const float tau = __uint_as_float((unsigned)(kthw >> 32));
+  const float R = __fmul_ru(__fsqrt_ru(tau), 1.000001f);
+  const float lox = __fsub_rd(q.x, R), loy = __fsub_rd(q.y, R), loz = __fsub_rd(q.z, R);
+  const float hix = __fadd_ru(q.x, R), hiy = __fadd_ru(q.y, R), hiz = __fadd_ru(q.z, R);
+  int lo = 0, cnt = 0;
+  {
+    unsigned ix0, iy0, iz0, ix1, iy1, iz1;
+    quantize(qn, lox, loy, loz, ix0, iy0, iz0);
+    quantize(qn, hix, hiy, hiz, ix1, iy1, iz1);
+    const unsigned ext = max(max(ix1 - ix0, iy1 - iy0), iz1 - iz0);
+    int sh = max(0, 30 - __clz((int)ext));
+    int ncx, ncy, ncz;
+    #pragma unroll 1
+    for (;; sh++) {
+      ncx = (int)(ix1 >> sh) - (int)(ix0 >> sh) + 1; ncy = (int)(iy1 >> sh) - (int)(iy0 >> sh) + 1; ncz = (int)(iz1 >> sh) - (int)(iz0 >> sh) + 1;
+      if (ncx * ncy * ncz <= 32 || sh >= MORTON_BITS) break;
+    }
+    if (lane < ncx * ncy * ncz) {
+      const unsigned cx = (ix0 >> sh) + (unsigned)(lane % ncx), cy = (iy0 >> sh) + (unsigned)((lane / ncx) % ncy), cz = (iz0 >> sh) + (unsigned)(lane / (ncx * ncy));
+      const unsigned long long pre = morton3(cx, cy, cz);
+      lo = lower_bound_bucketed(codes, bucket_start, pre << (3 * sh));
+      const int hi = (sh >= MORTON_BITS) ? n : lower_bound_bucketed(codes, bucket_start, (pre + 1ull) << (3 * sh));
+      cnt = hi - lo;
+    }
+  }
+  int incl = cnt;
+  #pragma unroll
+  for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
+  const int total = __shfl_sync(FULL, incl, 31);
+  const int excl = incl - cnt;
+  if (total > KNN_BOX_CAP) return knn_warp_query_levels(sorted, codes, bucket_start, n, k, qn, j, q);   // loose bound (a jump of the Morton curve)
+  #pragma unroll 1
+  for (int base = 0; base < total; base += 32) {
+    const int g = base + lane;
+    int o = 0, b = 31;
+    #pragma unroll
+    for (int s = 0; s < 5; s++) {
+      const int mid = (o + b) >> 1;
+      const int v = __shfl_sync(FULL, incl, mid);
+      if (v <= g) o = mid + 1; else b = mid;
+    }
+    const int cell_lo = __shfl_sync(FULL, lo, o), cell_ex = __shfl_sync(FULL, excl, o);
+    unsigned long long key = KEY_INF;
+    if (g < total) {
+      const int pos = cell_lo + (g - cell_ex);
+      if ((unsigned)(pos - wlo) >= (unsigned)wcnt) {            // window entries are in the list already
+        const float4 p = __ldg(sorted + pos);
+        if (p.x >= lox && p.x <= hix && p.y >= loy && p.y <= hiy && p.z >= loz && p.z <= hiz) key = key_of(p);
+      }
+    }
+    knn_warp_merge(top, key, k, false);
   }
   return top;
 }
@@ -993,7 +1115,7 @@ size_t cov_cub_temp_bytes(int n, int n_clouds) {
 cudaError_t launch_sort_cloud(const float4* pts, int n, const CovScratch& s, bool bucket_table, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
   const int tb = 256, nb = (n + tb - 1) / tb;
-  CloudRef ref; ref.arr = nullptr; ref.one.pts = pts; ref.one.cov6 = nullptr; ref.one.knn_out = nullptr; ref.one.n = n; ref.one.off = 0; ref.one.chunk_off = 0;
+  CloudRef ref; ref.arr = nullptr; ref.one.pts = pts; ref.one.cov6 = nullptr; ref.one.knn_out = nullptr; ref.one.n = n; ref.one.off = 0; ref.one.chunk_off = 0; ref.one.shard_rank = 0; ref.one.shard_world = 1;
   bbox_init_kernel<<<1, 32, 0, stream>>>(s.bbox, 1);
   bbox_kernel<<<min(nb, 148), tb, 0, stream>>>(ref, s.bbox);
   morton_kernel<<<nb, tb, 0, stream>>>(ref, s.bbox, s.codes_in, s.idx_in);
@@ -1058,7 +1180,7 @@ cudaError_t launch_covariances_group(const KnnGroup& g, cudaStream_t stream, int
   bucket_table_kernel<<<dim3((N_BUCKETS + 1 + tb - 1) / tb, nc), tb, 0, stream>>>(ref, g.s.codes_a, g.s.bucket_start);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   int total_chunks = 0;
-  for (int c = 0; c < g.n_clouds; c++) total_chunks += (g.clouds[c].n + 31) / 32;   // == the chunk_off prefix the caller filled in
+  for (int c = 0; c < g.n_clouds; c++) total_chunks += knn_owned_chunks(g.clouds[c].n, g.clouds[c].shard_rank, g.clouds[c].shard_world);   // == the chunk_off prefix the caller filled in
   if (g.k <= 8) e = launch_chunk<8>(g, total_chunks, stream);
   else if (g.k <= 12) e = launch_chunk<12>(g, total_chunks, stream);
   else if (g.k <= 16) e = launch_chunk<16>(g, total_chunks, stream);

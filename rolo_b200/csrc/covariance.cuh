@@ -30,6 +30,9 @@ struct KnnCloud {
   int n;
   int off;                    // first element of this cloud in the concatenated scratch arrays
   int chunk_off;              // number of 32-query chunks in the clouds before this one
+  int shard_rank, shard_world; // queries = the sorted positions of the blocks (KNN_SHARD_BLOCK points) with index = rank mod world; world <= 1: all.
+                              // A target-sharded registration deals the Morton order out in blocks, round-robin over the ranks (the expensive
+                              // queries cluster in space, so contiguous slices would be badly balanced); the index always covers the whole cloud
 };
 
 struct KnnScratch {           // device pointers; `total` = sum of n over the group
@@ -57,6 +60,17 @@ struct KnnGroup {
   unsigned long long* stats = nullptr;   // optional device counters [8] (development: ROLO_KNN_STATS=1)
 };
 constexpr int KNN_MAX_CLOUDS = 4096;
+constexpr int KNN_SHARD_BLOCK = 2048;   // points per dealt block of a sharded query set (64 chunks of 32)
+// number of 32-query chunks rank `rank` of `world` owns in a cloud of n points
+inline int knn_owned_chunks(int n, int rank, int world) {
+  const int chunks = (n + 31) / 32;
+  if (world <= 1) return chunks;
+  const int per = KNN_SHARD_BLOCK / 32, blocks = (chunks + per - 1) / per;
+  int own = 0;
+  for (int b = rank; b < blocks; b += world) own += (b == blocks - 1) ? chunks - b * per : per;
+  return own;
+}
+__host__ __device__ inline bool knn_owns(int sorted_pos, int rank, int world) { return world <= 1 || (sorted_pos / KNN_SHARD_BLOCK) % world == rank; }
 
 // index build + chunk-cooperative exact kNN + fused covariance/regulariser epilogue + fallback pass. `own_launches` receives
 // the number of this library's kernels that were launched (cub's are not counted).

@@ -37,12 +37,13 @@ __global__ void vox_clear_kernel(BuildRef ref) {
 
 __global__ void vox_insert_kernel(BuildRef ref) {
   const VoxelBuild& B = get_build(ref);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;          // work item: point i, or sorted position i of a restricted build
   if (i >= B.n) return;
   VoxSlot* table = B.table;
   const unsigned mask = B.mask;
   int* counters = B.counters;
-  const float4 p = B.pts[i];
+  if (B.order && !knn_owns(i, B.shard_rank, B.shard_world)) { B.slot_of_point[i] = -1; return; }
+  const float4 p = B.order ? B.order[i] : B.pts[i];
   int cx, cy, cz;
   voxel_coord(B.grid, (double)p.x, (double)p.y, (double)p.z, cx, cy, cz);
   // a point without a finite key (NaN / Inf coordinates, the origin of a polar grid) sits in an unreachable cell of the
@@ -79,17 +80,18 @@ __global__ void vox_accumulate_kernel(BuildRef ref) {
   const VoxelBuild& B = get_build(ref);
   const int n = B.n;
   if ((int)(blockIdx.x * blockDim.x) >= n) return;          // block-uniform
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31;
   int id = -1;
   double v[10];
   #pragma unroll
   for (int k = 0; k < 10; k++) v[k] = 0.0;
-  if (i < n) {
-    const int slot = B.slot_of_point[i];
+  if (t < n) {
+    const int slot = B.slot_of_point[t];
     if (slot >= 0) {
       id = B.table[slot].id;
-      const float4 p = B.pts[i];
+      const float4 p = B.order ? B.order[t] : B.pts[t];
+      const int i = B.order ? __float_as_int(p.w) : t;      // the covariance lives at the point's original index
       const size_t base = (size_t)(i / TILE_PTS) * COV_PLANES * TILE_PTS + (i % TILE_PTS);
       v[0] = (double)p.x; v[1] = (double)p.y; v[2] = (double)p.z;
       #pragma unroll
@@ -133,7 +135,51 @@ __global__ void vox_finalize_kernel(BuildRef ref) {
   B.vox[id] = p;
 }
 
-cudaError_t launch_all(const BuildRef& ref, int n_builds, int max_n, unsigned max_mask, cudaStream_t stream) {
+__global__ void vox_keys_kernel(const VoxSlot* __restrict__ table, size_t cap, unsigned long long* __restrict__ keys) {
+  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (size_t)gridDim.x * blockDim.x) {
+    const VoxSlot sl = table[s];
+    if (sl.key != KEY_EMPTY && sl.id >= 0) keys[sl.id] = sl.key;
+  }
+}
+
+// import, pass 1: every gathered entry claims (or finds) the slot of its key; the creator takes the next id and zeroes its row
+__global__ void vox_import_insert_kernel(VoxelBuild B, const unsigned long long* __restrict__ keys, int n_entries, int* __restrict__ slot_of_entry) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_entries) return;
+  const unsigned long long key = keys[e];
+  unsigned h = hash_key(key) & B.mask;
+  for (unsigned probe = 0; probe <= B.mask; probe++) {
+    unsigned long long* kp = &B.table[h].key;
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
+    if (cur == KEY_EMPTY) {
+      cur = atomicCAS(kp, KEY_EMPTY, key);
+      if (cur == KEY_EMPTY) {
+        const int id = atomicAdd(&B.counters[0], 1);
+        B.table[h].id = id;
+        double* row = B.sums + (size_t)id * 10;
+        #pragma unroll
+        for (int k = 0; k < 10; k++) row[k] = 0.0;
+        slot_of_entry[e] = (int)h;
+        return;
+      }
+    }
+    if (cur == key) { slot_of_entry[e] = (int)h; return; }
+    h = (h + 1) & B.mask;
+  }
+  atomicExch(&B.counters[1], 2);
+  slot_of_entry[e] = -1;
+}
+// import, pass 2: add the entry's 10 sums to its voxel's row
+__global__ void vox_import_add_kernel(VoxelBuild B, const double* __restrict__ sums_in, int n_entries, const int* __restrict__ slot_of_entry) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int e = t / 10, k = t % 10;
+  if (e >= n_entries) return;
+  const int slot = slot_of_entry[e];
+  if (slot < 0) return;
+  atomicAdd(B.sums + (size_t)B.table[slot].id * 10 + k, sums_in[(size_t)e * 10 + k]);
+}
+
+cudaError_t launch_all(const BuildRef& ref, int n_builds, int max_n, unsigned max_mask, cudaStream_t stream, bool finalize = true) {
   if (n_builds <= 0) return cudaSuccess;
   const int threads = 256;
   const unsigned nb = (unsigned)std::max(1, (max_n + threads - 1) / threads);
@@ -143,16 +189,35 @@ cudaError_t launch_all(const BuildRef& ref, int n_builds, int max_n, unsigned ma
   if (max_n > 0) {
     vox_insert_kernel<<<dim3(nb, n_builds), threads, 0, stream>>>(ref);
     vox_accumulate_kernel<<<dim3(nb, n_builds), threads, 0, stream>>>(ref);
-    vox_finalize_kernel<<<dim3(nb, n_builds), threads, 0, stream>>>(ref);
+    if (finalize) vox_finalize_kernel<<<dim3(nb, n_builds), threads, 0, stream>>>(ref);
   }
   return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t launch_voxel_build(const VoxelBuild& b, cudaStream_t stream) {
+cudaError_t launch_voxel_build(const VoxelBuild& b, cudaStream_t stream, bool finalize) {
   BuildRef ref; ref.arr = nullptr; ref.one = b;
-  return launch_all(ref, 1, b.n, b.mask, stream);
+  return launch_all(ref, 1, b.n, b.mask, stream, finalize);
+}
+
+cudaError_t launch_voxel_keys(const VoxelBuild& b, unsigned long long* keys, cudaStream_t stream) {
+  const size_t cap = (size_t)b.mask + 1;
+  vox_keys_kernel<<<(unsigned)std::min<size_t>((cap + 255) / 256, 2048), 256, 0, stream>>>(b.table, cap, keys);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_voxel_import(const VoxelBuild& b, const unsigned long long* keys, const double* sums_in, int n_entries, cudaStream_t stream) {
+  BuildRef ref; ref.arr = nullptr; ref.one = b;
+  const size_t cap = (size_t)b.mask + 1;
+  vox_clear_kernel<<<dim3((unsigned)std::min<size_t>((cap + 255) / 256, 2048), 1), 256, 0, stream>>>(ref);
+  if (n_entries > 0) {
+    vox_import_insert_kernel<<<(n_entries + 255) / 256, 256, 0, stream>>>(b, keys, n_entries, b.slot_of_point);
+    vox_import_add_kernel<<<(n_entries * 10 + 255) / 256, 256, 0, stream>>>(b, sums_in, n_entries, b.slot_of_point);
+    BuildRef fin = ref; fin.one.order = nullptr; fin.one.n = std::min(n_entries, b.n);
+    vox_finalize_kernel<<<dim3((unsigned)((fin.one.n + 255) / 256), 1), 256, 0, stream>>>(fin);
+  }
+  return cudaGetLastError();
 }
 
 // every target of a batch in one launch chain: `dev_builds` is the device copy of `host_builds`

@@ -294,6 +294,29 @@ class RotVGICP:
         assert len(blob) == 64 * world
         self._ck(self._L.rg_shard_connect(self._h, rank, world, blob))
 
+    def setTargetShard(self, rank: int, world: int):
+        """Target-sharded setup (config 4): this rank estimates covariances / accumulates voxels for its slice of the target only."""
+        self._ck(self._L.rg_set_target_shard(self._h, int(rank), int(world)))
+
+    def setVoxelMergeHook(self, fn):
+        """fn(keys_ptr:int, sums_ptr:int, n_local:int, stream:int) -> int; must call voxelImport() with the list gathered over all ranks."""
+        if fn is None:
+            self._merge_hook = None
+            self._ck(self._L.rg_set_voxel_merge_hook(self._h, capi.VOXEL_MERGE_FN(0), None))
+            return
+
+        def tramp(user, keys, sums, n_local, stream):
+            try:
+                return int(fn(keys or 0, sums or 0, int(n_local), stream or 0) or 0)
+            except Exception as e:   # never let an exception cross the C boundary
+                print("voxel merge hook failed:", repr(e))
+                return -1
+        self._merge_hook = capi.VOXEL_MERGE_FN(tramp)
+        self._ck(self._L.rg_set_voxel_merge_hook(self._h, self._merge_hook, None))
+
+    def voxelImport(self, keys_ptr: int, sums_ptr: int, n_total: int):
+        self._ck(self._L.rg_voxel_import(self._h, C.c_void_p(keys_ptr), C.c_void_p(sums_ptr), int(n_total)))
+
     def setReduceHook(self, fn, on_device: bool):
         """Sharded registration (config 4): fn(buf_ptr:int, count:int, on_device:bool, stream:int) -> int."""
         if fn is None:

@@ -2,12 +2,45 @@
 // with the exact statement sequence of LidarOdometry::scanRegeistration (src/lidarOdometry.cpp:448-501 of the reference).
 // Built by tests/test_gpu_cpp_dropin.py against oracle/ref_shim (the image has no PCL/Eigen; a ROLO checkout would use its
 // own) and linked with librolo_gicp_b200.so. Prints the rotation estimate and the translation result.
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
 
 #include <pcl/common/transforms.h>
 #include <rot_gicp/gicp/rot_vgicp.hpp>
+#include <rot_gicp/so3/so3.hpp>
+
+// A USER subclass of the base class, as the reference's layout allows (lsq_registration.hpp:48-106): point-to-point cost against a
+// fixed correspondence (point i of the source to point i of the target), J = [skew(p') | -I] like rot_vgicp_impl.hpp:265-267.
+// It only implements the protected virtuals; align() and the whole Gauss-Newton / LM logic come from fast_gicp::LsqRegistration.
+template <typename PointT>
+class PointToPoint : public fast_gicp::LsqRegistration<PointT, PointT> {
+ public:
+  using Base = fast_gicp::LsqRegistration<PointT, PointT>;
+  using PointCloudTargetConstPtr = typename Base::PointCloudTargetConstPtr;
+  void setInputTarget(const PointCloudTargetConstPtr& cloud) override { tgt_ = cloud; }
+ protected:
+  PointCloudTargetConstPtr tgt_;
+  double linearize(const Eigen::Isometry3d& trans, Eigen::Matrix<double, 6, 6>* H, Eigen::Matrix<double, 6, 1>* b) override {
+    double cost = 0.0;
+    if (H && b) { H->setZero(); b->setZero(); }
+    const Eigen::Matrix4d T = trans.matrix();
+    for (size_t i = 0; i < this->input_->size(); i++) {
+      const auto& s = this->input_->points[i]; const auto& t = tgt_->points[i];
+      const double px = T(0,0)*s.x + T(0,1)*s.y + T(0,2)*s.z + T(0,3), py = T(1,0)*s.x + T(1,1)*s.y + T(1,2)*s.z + T(1,3), pz = T(2,0)*s.x + T(2,1)*s.y + T(2,2)*s.z + T(2,3);
+      const double e[3] = {t.x - px, t.y - py, t.z - pz};
+      cost += e[0]*e[0] + e[1]*e[1] + e[2]*e[2];
+      if (H && b) {
+        const double J[3][6] = {{0, -pz, py, -1, 0, 0}, {pz, 0, -px, 0, -1, 0}, {-py, px, 0, 0, 0, -1}};
+        for (int r = 0; r < 3; r++) for (int a = 0; a < 6; a++) { (*b)(a) += J[r][a] * e[r]; for (int c = 0; c < 6; c++) (*H)(a, c) += J[r][a] * J[r][c]; }
+      }
+    }
+    return cost;
+  }
+  double compute_error(const Eigen::Isometry3d& trans) override { return linearize(trans, nullptr, nullptr); }
+  double compute_t_error(const Eigen::Vector3d&, const Eigen::Vector3d&, const Eigen::Vector3d&, const double&, const double&) override { return 0.0; }
+};
 
 using PointType = pcl::PointXYZI;
 
@@ -62,5 +95,22 @@ int main(int argc, char** argv) {
   Eigen::Matrix<double, 6, 6> H; Eigen::Matrix<double, 6, 1> b;
   double c = rot_vgicp.evaluateCost(Eigen::Matrix4f::Identity(), &H, &b);
   std::printf("cost=%.6f H00=%.6f covs=%zu\n", c, H(0, 0), rot_vgicp.getSourceCovariances().size());
+  // the base class on its own: a user subclass recovers a known rigid motion through the inherited align() (no GPU involved)
+  {
+    Eigen::Matrix<double, 6, 1> a; a << 0.03, -0.02, 0.05, 0.2, -0.1, 0.05;
+    const Eigen::Matrix4f Tgt = fast_gicp::se3_exp(a).matrix().cast<float>();
+    pcl::PointCloud<PointType>::Ptr src(new pcl::PointCloud<PointType>), dst(new pcl::PointCloud<PointType>), out(new pcl::PointCloud<PointType>);
+    src->resize(200);
+    for (size_t i = 0; i < src->size(); i++) { src->points[i].x = std::sin(0.37 * i) * 5.0f; src->points[i].y = std::cos(0.11 * i) * 4.0f; src->points[i].z = std::sin(0.05 * i + 1.0) * 2.0f; }
+    pcl::transformPointCloud(*src, *dst, Tgt);
+    PointToPoint<PointType> p2p;
+    p2p.setOptimizerType(fast_gicp::LSQ_OPTIMIZER_TYPE::LevenbergMarquardt);
+    p2p.setInputTarget(dst); p2p.setInputSource(src);
+    p2p.align(*out);
+    const Eigen::Matrix4f Tr = p2p.getFinalTransformation();
+    float err = 0.f;
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) err = std::max(err, std::abs(Tr(i, j) - Tgt(i, j)));
+    std::printf("subclass converged=%d err=%.3e\n", (int)p2p.hasConverged(), err);
+  }
   return 0;
 }

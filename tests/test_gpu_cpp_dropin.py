@@ -40,5 +40,7 @@ def test_drop_in_sequence_matches_python(tmp_path):
     assert "converged=1" in out and "alias=invalid_argument" in out and f"covs={len(src)}" in out
     assert np.allclose(nums[:3], T[0, :3], atol=2e-6) and np.allclose(nums[3:6], t, atol=2e-6)
     assert np.allclose(nums[6:9], src[0, :3] + t.astype(np.float32), atol=1e-4)
+    m = re.search(r"subclass converged=(\d) err=(\S+)", out)     # a user subclass of fast_gicp::LsqRegistration through the inherited align()
+    assert m and m.group(1) == "1" and float(m.group(2)) < 1e-4
     fit = float(re.search(r"fitness=(\S+)", out).group(1))
     assert abs(fit - r.getFitnessScore(T)) <= 1e-9 * fit      # output cloud = input + translation (lsq.hpp:75-78)

@@ -28,8 +28,9 @@ def configure(r):
 
 
 ok = True
-for on_device, transport in ((True, "p2p"), (True, "nccl"), (False, "nccl")):
-    r = sharded_registration(tgt, src, rank, world, device=local, on_device=on_device, group=None if on_device else gloo, transport=transport)
+for on_device, transport, shard_target in ((True, "p2p", False), (True, "nccl", False), (False, "nccl", False), (True, "p2p", True)):
+    r = sharded_registration(tgt, src, rank, world, device=local, on_device=on_device, group=None if on_device else gloo, transport=transport,
+                             shard_target=shard_target)
     configure(r)
     t0 = time.perf_counter(); T = r.align(); dt = time.perf_counter() - t0
     Td = r.getFinalPoseDouble()
@@ -41,10 +42,11 @@ for on_device, transport in ((True, "p2p"), (True, "nccl"), (False, "nccl")):
     t = torch.tensor(Td.ravel(), device="cuda"); tmax = t.clone(); tmin = t.clone()
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     spread = float((tmax - tmin).abs().max())
+    # a merged voxel map adds the same numbers in another order: 1e-9 instead of bit equality with the single-GPU run
     good = drot <= 1e-9 and dtr <= 1e-9 and same_iters and spread == 0.0
     ok = ok and good
     if rank == 0:
-        print(f"transport={transport} on_device={on_device}: world={world} pose vs single-GPU {drot:.2e} rad {dtr:.2e} m, iters {r.nrIterations()} vs {ref.nrIterations()}, "
+        print(f"transport={transport} on_device={on_device} shard_target={shard_target}: world={world} pose vs single-GPU {drot:.2e} rad {dtr:.2e} m, iters {r.nrIterations()} vs {ref.nrIterations()}, "
               f"rank spread {spread:.1e}, align {1e3*dt:.2f} ms -> {'OK' if good else 'FAIL'}")
 dist.barrier()
 dist.destroy_process_group()
