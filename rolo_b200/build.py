@@ -57,6 +57,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(SRC, s))]
     if not force and not _stale(LIB, _deps()):
+        if not os.path.exists(ALIAS):
+            _alias()
         return LIB
     with cf.ThreadPoolExecutor(max_workers=len(srcs)) as ex:
         objs = list(ex.map(lambda s: _compile(s, verbose), srcs))
@@ -64,7 +66,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    _alias()
     return LIB
+
+
+ALIAS = os.path.join(OUT_DIR, "librot_gicp.so")   # the reference's library name (CMakeLists.txt:160): `target_link_libraries(... rot_gicp)` resolves to it
+
+
+def _alias():
+    try:
+        if os.path.islink(ALIAS) or os.path.exists(ALIAS):
+            os.remove(ALIAS)
+        os.symlink(os.path.basename(LIB), ALIAS)
+    except OSError:
+        pass
 
 
 if __name__ == "__main__":

@@ -59,6 +59,7 @@ __global__ void bbox_kernel(CloudRef ref, int* bbox_all) {
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C.n; i += gridDim.x * blockDim.x) {
     const float4 p = pts[i];
+    if (!((p.x - p.x == 0.f) && (p.y - p.y == 0.f) && (p.z - p.z == 0.f))) continue;   // NaN / Inf points must not blow up the box
     mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
     mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
   }

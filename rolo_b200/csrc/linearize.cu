@@ -202,9 +202,14 @@ linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict_
       if (i < n) {
         const double px = (double)pf.x, py = (double)pf.y, pz = (double)pf.z;
         // p' = R p + t
-        const double x = s_dyn.R[0] * px + s_dyn.R[1] * py + s_dyn.R[2] * pz + s_dyn.t[0];
-        const double y = s_dyn.R[3] * px + s_dyn.R[4] * py + s_dyn.R[5] * pz + s_dyn.t[1];
-        const double z = s_dyn.R[6] * px + s_dyn.R[7] * py + s_dyn.R[8] * pz + s_dyn.t[2];
+        double x = s_dyn.R[0] * px + s_dyn.R[1] * py + s_dyn.R[2] * pz + s_dyn.t[0];
+        double y = s_dyn.R[3] * px + s_dyn.R[4] * py + s_dyn.R[5] * pz + s_dyn.t[1];
+        double z = s_dyn.R[6] * px + s_dyn.R[7] * py + s_dyn.R[8] * pz + s_dyn.t[2];
+        // a point without a usable voxel key never matches in the reference (NaN / Inf coordinates from a non-dense cloud, or the exact
+        // origin of a polar grid, whose acos(z/r) is NaN: x86 turns those into the unreachable cell INT_MIN). It is taken out here,
+        // with its coordinates zeroed, so that 0 * NaN cannot poison the sums of the whole pair
+        const bool usable = (x - x == 0.0) && (y - y == 0.0) && (z - z == 0.0) && (s_grid.voxel_type != 0 || x != 0.0 || y != 0.0 || z != 0.0);
+        if (!usable) { x = 0.0; y = 0.0; z = 0.0; }
 
         int cx = 0, cy = 0, cz = 0;
         ulonglong2 slot0 = make_ulonglong2(KEY_EMPTY, 0ull);
@@ -215,7 +220,7 @@ linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict_
           // issue the first probe (offset 0) now; it is consumed after C_A has been computed
           int dx0, dy0, dz0;
           neighbor_offset<NOFF>(0, dx0, dy0, dz0);
-          key_ok = key_in_range(cx + dx0, cy + dy0, cz + dz0);
+          key_ok = usable && key_in_range(cx + dx0, cy + dy0, cz + dz0);
           if (key_ok) { h0 = hash_key(pack_key(cx + dx0, cy + dy0, cz + dz0)) & mask; slot0 = __ldg(reinterpret_cast<const ulonglong2*>(table + h0)); }
         } else if (NOFF == 1) {
           slot0.y = (unsigned long long)(unsigned)corr[i];
@@ -256,7 +261,7 @@ linearize_kernel(const LinStatic* __restrict__ st_arr, const LinDyn* __restrict_
             } else {
               int dx, dy, dz;
               neighbor_offset<NOFF>(o, dx, dy, dz);
-              id = table_lookup(table, mask, cx + dx, cy + dy, cz + dz);
+              id = usable ? table_lookup(table, mask, cx + dx, cy + dy, cz + dz) : -1;
             }
             corr[(size_t)i * NOFF + o] = id;
           } else {

@@ -149,3 +149,29 @@ def test_per_frame_object_lifecycle_is_leak_free(tiny_pair):
         assert np.array_equal(T, T0) and np.array_equal(t, t0)
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 8 * 1024 * 1024
+
+
+def test_non_finite_and_origin_points_never_match(tiny_pair):
+    """pcl clouds with is_dense = false carry NaN points, and invalid lidar returns are often encoded as the origin. In the reference such
+    a point never finds a voxel (its key is the unreachable INT_MIN cell) and is simply skipped; here it must not poison the sums either."""
+    tgt, src, T_gt = tiny_pair
+    bad = src.copy()
+    bad[5, :3] = np.nan; bad[77, 0] = np.inf; bad[300, :3] = 0.0
+    keep = np.ones(len(src), bool); keep[[5, 77, 300]] = False
+    tbad = tgt.copy(); tbad[11, :3] = np.nan; tbad[200, :3] = 0.0
+    tkeep = np.ones(len(tgt), bool); tkeep[[11, 200]] = False
+
+    def make(t, s):
+        r = RotVGICP(); r.setPolarResolution(0.175, 0.175, 2.0); r.setInputTarget(t); r.setInputSource(s)
+        return r
+    a = make(tbad, bad); b = make(tgt[tkeep], src[keep])
+    ca, Ha, ba = a.linearize(T_gt); cb, Hb, bb = b.linearize(T_gt)
+    assert np.isfinite(ca) and np.all(np.isfinite(Ha)) and np.all(np.isfinite(ba))
+    # the neighbourhoods of the finite points differ slightly (three source / two target points are gone from b), so the sums agree
+    # only approximately; what must hold exactly is the number of correspondences: none of the bad points matched
+    assert a.numCorrespondences() <= b.numCorrespondences() + 0 and a.numCorrespondences() >= b.numCorrespondences() - 8
+    assert abs(ca - cb) <= 2e-2 * abs(cb)
+    ka, _, _, na = a.getVoxels(); kb, _, _, nb = b.getVoxels()
+    assert int(na.sum()) == int(nb.sum()) == int(tkeep.sum())          # the NaN and the origin target point were not inserted
+    Ta = a.align(); Tb = b.align()
+    assert np.all(np.isfinite(Ta)) and np.max(np.abs(Ta - Tb)) <= 1e-3
