@@ -204,6 +204,11 @@ int rg_set_target_shard(rg_ctx*, int rank, int world);
 int rg_set_voxel_merge_hook(rg_ctx*, rg_voxel_merge_fn fn, void* user);
 int rg_voxel_import(rg_ctx*, const void* keys_dev, const void* sums_dev, int n_total);
 
+/* Deterministic voxel build: the target points are radix-sorted by voxel key and every voxel adds its points in index order (the order
+ * of the reference's serial loop, vmp_voxel.hpp:167-197) instead of fp64 atomics in arrival order: means, covariances and voxel ids
+ * are then bit-reproducible from run to run (and the sums equal the oracle's bit for bit). Slower; for tests and for ranks that must
+ * agree to the last bit. Stand-alone contexts only (a batch always uses the atomic build). */
+int rg_set_deterministic(rg_ctx*, int on);
 /* voxelmap_.reset() (rot_vgicp_impl.hpp:147): the next linearize rebuilds the voxel map from the target and its covariances */
 int rg_reset_voxelmap(rg_ctx*);
 

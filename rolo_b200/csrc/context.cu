@@ -312,8 +312,21 @@ int build_voxelmap(rg_ctx* c) {
     if (!c->voxel_ok) return set_err(c, RG_ERR_INVALID, "voxel merge hook returned without calling rg_voxel_import");
     return RG_OK;
   }
-  RG_CUDA(c, launch_voxel_build(b, c->stream));
-  g_launches += 4;
+  if (c->deterministic) {
+    const int n = b.n;
+    RG_CUDA(c, c->codes_in.ensure(c->device, n)); RG_CUDA(c, c->codes_out.ensure(c->device, n));
+    RG_CUDA(c, c->idx_in.ensure(c->device, (size_t)n + 1)); RG_CUDA(c, c->idx_out.ensure(c->device, n));
+    RG_CUDA(c, c->det_flags.ensure(c->device, (size_t)n + 1));
+    VoxelDetScratch s;
+    s.cub_temp_bytes = voxel_det_temp_bytes(n);
+    RG_CUDA(c, c->cub_temp.ensure(c->device, s.cub_temp_bytes));
+    s.keys_a = c->codes_in.p; s.keys_b = c->codes_out.p; s.idx_a = c->idx_in.p; s.idx_b = c->idx_out.p; s.flags = c->det_flags.p; s.cub_temp = c->cub_temp.p;
+    RG_CUDA(c, launch_voxel_build_deterministic(b, s, c->stream));
+    g_launches += 4;
+  } else {
+    RG_CUDA(c, launch_voxel_build(b, c->stream));
+    g_launches += 4;
+  }
   c->voxel_ok = true; c->n_vox = -1; c->st_ok = false; c->have_corr = false;
   return RG_OK;
 }
@@ -570,7 +583,7 @@ void rg_destroy(rg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   c->src.release(); c->tgt.release();
   c->table.release(); c->vox.release(); c->sums.release(); c->slot_of_point.release(); c->counters.release();
-  c->codes_in.release(); c->codes_out.release(); c->idx_in.release(); c->idx_out.release(); c->bbox.release(); c->sorted.release(); c->cub_temp.release(); c->knn_idx.release(); c->bucket_start.release(); c->knn.release(); c->vox_keys.release();
+  c->codes_in.release(); c->codes_out.release(); c->idx_in.release(); c->idx_out.release(); c->bbox.release(); c->sorted.release(); c->cub_temp.release(); c->knn_idx.release(); c->bucket_start.release(); c->knn.release(); c->vox_keys.release(); c->det_flags.release();
   c->fe_raw.release(); c->fe_owner.release(); c->fe_row_count.release(); c->fe_col.release(); c->fe_start.release(); c->fe_end.release();
   c->fe_counts.release(); c->fe_picked.release(); c->fe_label.release(); c->fe_corner_cnt.release(); c->fe_surf_cnt.release();
   c->fe_range_image.release(); c->fe_prange.release(); c->fe_curv.release(); c->fe_full.release(); c->fe_extracted.release();
@@ -701,6 +714,8 @@ int rg_calculate_covariances(rg_ctx* c, int which) {
   if (rc == RG_OK && which == RG_TARGET) { c->voxel_ok = false; c->st_ok = false; }
   return rc;
 }
+
+int rg_set_deterministic(rg_ctx* c, int on) { CHECK_CTX(c); c->deterministic = on != 0; c->voxel_ok = false; c->st_ok = false; c->have_corr = false; return RG_OK; }
 
 int rg_reset_voxelmap(rg_ctx* c) { CHECK_CTX(c); c->voxel_ok = false; c->st_ok = false; c->have_corr = false; return RG_OK; }
 

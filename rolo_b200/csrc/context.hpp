@@ -235,6 +235,8 @@ struct rg_ctx {
   double last_kernel_us = -1.0;
 
   rg_reduce_fn reduce_fn = nullptr; void* reduce_user = nullptr; int reduce_on_device = 0;
+  bool deterministic = false;           // rg_set_deterministic: sort + fixed-order voxel sums instead of fp64 atomics
+  DevBuf<int> det_flags;
   int tgt_rank = 0, tgt_world = 0;      // target-sharded setup (rg_set_target_shard): this rank's slice of the target's Morton order
   rg_voxel_merge_fn voxel_merge_fn = nullptr; void* voxel_merge_user = nullptr;
   DevBuf<unsigned long long> vox_keys;

@@ -14,6 +14,8 @@
 
 #include "voxelmap.cuh"
 #include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 namespace rolo {
 
@@ -179,6 +181,62 @@ __global__ void vox_import_add_kernel(VoxelBuild B, const double* __restrict__ s
   atomicAdd(B.sums + (size_t)B.table[slot].id * 10 + k, sums_in[(size_t)e * 10 + k]);
 }
 
+// ---- deterministic build --------------------------------------------------------------------------------------------------
+__global__ void vox_det_key_kernel(VoxelBuild B, unsigned long long* __restrict__ keys, int* __restrict__ idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n) return;
+  const float4 p = B.pts[i];
+  int cx, cy, cz;
+  voxel_coord(B.grid, (double)p.x, (double)p.y, (double)p.z, cx, cy, cz);
+  const bool finite = (p.x - p.x == 0.f) && (p.y - p.y == 0.f) && (p.z - p.z == 0.f) &&
+                      (B.grid.voxel_type != 0 || (p.x != 0.f || p.y != 0.f || p.z != 0.f));
+  unsigned long long key = KEY_EMPTY;                       // sorts behind every real key (21-bit fields: the top bit is never set)
+  if (finite) {
+    if (key_in_range(cx, cy, cz)) key = pack_key(cx, cy, cz); else atomicExch(&B.counters[1], 1);
+  }
+  keys[i] = key; idx[i] = i;
+}
+__global__ void vox_det_head_kernel(const unsigned long long* __restrict__ keys, int n, int* __restrict__ flags) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j > n) return;
+  flags[j] = (j < n && keys[j] != KEY_EMPTY && (j == 0 || keys[j] != keys[j - 1])) ? 1 : 0;   // flags[n] = 0: its exclusive sum is the voxel count
+}
+// one thread per voxel: sequential fp64 sums over its points in index order, payload row, table entry with id = rank of the key
+__global__ void vox_det_reduce_kernel(VoxelBuild B, const unsigned long long* __restrict__ keys, const int* __restrict__ idx,
+                                      const int* __restrict__ rank /* exclusive sum of the head flags */) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) B.counters[0] = rank[B.n];
+  if (j >= B.n) return;
+  const unsigned long long key = keys[j];
+  if (key == KEY_EMPTY || (j > 0 && keys[j - 1] == key)) return;      // not the first point of a voxel
+  const int id = rank[j];
+  double v[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int e = j; e < B.n && keys[e] == key; e++) {
+    const int i = idx[e];
+    const float4 p = B.pts[i];
+    const size_t base = (size_t)(i / TILE_PTS) * COV_PLANES * TILE_PTS + (i % TILE_PTS);
+    v[0] += (double)p.x; v[1] += (double)p.y; v[2] += (double)p.z;
+    #pragma unroll
+    for (int c = 0; c < 6; c++) v[3 + c] += (double)B.cov6[base + (size_t)c * TILE_PTS];
+    v[9] += 1.0;
+  }
+  double* row = B.sums + (size_t)id * 10;
+  #pragma unroll
+  for (int k = 0; k < 10; k++) row[k] = v[k];
+  VoxPayload pl;
+  pl.mean[0] = v[0] / v[9]; pl.mean[1] = v[1] / v[9]; pl.mean[2] = v[2] / v[9];
+  #pragma unroll
+  for (int c = 0; c < 6; c++) pl.cov[c] = v[3 + c] / v[9];
+  pl.w = sqrt(v[9]);
+  B.vox[id] = pl;
+  unsigned h = hash_key(key) & B.mask;                              // keys are unique here: plain linear probing with CAS
+  for (unsigned probe = 0; probe <= B.mask; probe++) {
+    if (atomicCAS(&B.table[h].key, KEY_EMPTY, key) == KEY_EMPTY) { B.table[h].id = id; return; }
+    h = (h + 1) & B.mask;
+  }
+  atomicExch(&B.counters[1], 2);
+}
+
 cudaError_t launch_all(const BuildRef& ref, int n_builds, int max_n, unsigned max_mask, cudaStream_t stream, bool finalize = true) {
   if (n_builds <= 0) return cudaSuccess;
   const int threads = 256;
@@ -199,6 +257,33 @@ cudaError_t launch_all(const BuildRef& ref, int n_builds, int max_n, unsigned ma
 cudaError_t launch_voxel_build(const VoxelBuild& b, cudaStream_t stream, bool finalize) {
   BuildRef ref; ref.arr = nullptr; ref.one = b;
   return launch_all(ref, 1, b.n, b.mask, stream, finalize);
+}
+
+size_t voxel_det_temp_bytes(int n) {
+  size_t a = 0, c = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const int*)nullptr, (int*)nullptr, n, 0, 64);
+  cub::DeviceScan::ExclusiveSum(nullptr, c, (const int*)nullptr, (int*)nullptr, n + 1);
+  return std::max(a, c);
+}
+
+cudaError_t launch_voxel_build_deterministic(const VoxelBuild& b, const VoxelDetScratch& s, cudaStream_t stream) {
+  if (b.order) return cudaErrorInvalidValue;
+  BuildRef ref; ref.arr = nullptr; ref.one = b;
+  const size_t cap = (size_t)b.mask + 1;
+  vox_clear_kernel<<<dim3((unsigned)std::min<size_t>((cap + 255) / 256, 2048), 1), 256, 0, stream>>>(ref);
+  if (b.n <= 0) return cudaGetLastError();
+  const int nb = (b.n + 255) / 256;
+  vox_det_key_kernel<<<nb, 256, 0, stream>>>(b, s.keys_a, s.idx_a);
+  size_t temp = s.cub_temp_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(s.cub_temp, temp, s.keys_a, s.keys_b, s.idx_a, s.idx_b, b.n, 0, 64, stream);   // stable
+  if (e != cudaSuccess) return e;
+  vox_det_head_kernel<<<(b.n + 1 + 255) / 256, 256, 0, stream>>>(s.keys_b, b.n, s.flags);
+  temp = s.cub_temp_bytes;
+  int* rank = s.idx_a;                                                   // idx_a is free after the sort: [n + 1] needed -> the caller sizes it n + 1
+  e = cub::DeviceScan::ExclusiveSum(s.cub_temp, temp, s.flags, rank, b.n + 1, stream);
+  if (e != cudaSuccess) return e;
+  vox_det_reduce_kernel<<<nb, 256, 0, stream>>>(b, s.keys_b, s.idx_b, rank);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_voxel_keys(const VoxelBuild& b, unsigned long long* keys, cudaStream_t stream) {

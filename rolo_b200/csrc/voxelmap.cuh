@@ -23,6 +23,13 @@ struct VoxelBuild {
 };
 
 cudaError_t launch_voxel_build(const VoxelBuild& b, cudaStream_t stream, bool finalize = true);           // 4 kernels (3 without the finalize pass)
+// Deterministic build: points are radix-sorted by packed voxel key (stable: index order inside a voxel), one thread per
+// voxel adds its points in index order — the summation order of the reference's serial loop — and voxel ids are the ranks of the keys.
+// Bit-reproducible from run to run (the default build sums with fp64 atomics in arrival order). Scratch: keys_a/keys_b [n] u64, idx_a/idx_b [n]
+// int, flags [n + 1] int, cub temp (cov_cub_temp_bytes(n) is enough). Whole-cloud builds only.
+struct VoxelDetScratch { unsigned long long *keys_a, *keys_b; int *idx_a, *idx_b, *flags; void* cub_temp; size_t cub_temp_bytes; };
+size_t voxel_det_temp_bytes(int n);
+cudaError_t launch_voxel_build_deterministic(const VoxelBuild& b, const VoxelDetScratch& s, cudaStream_t stream);
 // compact per-voxel key list of a built map: keys[id] = packed key (rows of b.sums are already compact by id)
 cudaError_t launch_voxel_keys(const VoxelBuild& b, unsigned long long* keys, cudaStream_t stream);
 // rebuild the map from a list of (key, 10 sums) entries gathered over all ranks: entries with equal keys add up; then finalize

@@ -294,6 +294,10 @@ class RotVGICP:
         assert len(blob) == 64 * world
         self._ck(self._L.rg_shard_connect(self._h, rank, world, blob))
 
+    def setDeterministic(self, on: bool = True):
+        """Sort + fixed-order voxel sums (bit-reproducible voxel map) instead of fp64 atomics."""
+        self._ck(self._L.rg_set_deterministic(self._h, int(bool(on))))
+
     def setTargetShard(self, rank: int, world: int):
         """Target-sharded setup (config 4): this rank estimates covariances / accumulates voxels for its slice of the target only."""
         self._ck(self._L.rg_set_target_shard(self._h, int(rank), int(world)))

@@ -61,6 +61,35 @@ def test_voxelmap(small_pair, grid):
     assert np.max(np.abs(co6 - cg)) <= 1e-9     # same fp32-rounded inputs on both sides -> fp64 sums agree
 
 
+@pytest.mark.parametrize("grid", ["polar", "uniform"])
+def test_deterministic_voxelmap_is_bit_reproducible(small_pair, grid):
+    """rg_set_deterministic: points sorted by voxel key, every voxel summed in point-index order = the summation order of the reference's
+    serial loop (vmp_voxel.hpp:167-197). The map is then identical from run to run AND equal to the oracle's bit for bit; registrations on
+    it take the same optimiser decisions every time."""
+    tgt, src, _ = small_pair
+    o, g = make_both(tgt, src, uniform=1.0 if grid == "uniform" else None)
+    g.setDeterministic(True)
+    o.createVoxelmap(); g.create_voxelmap()
+    ko, mo, co, no = o.getVoxels()
+    kg, mg, cg, ng = g.getVoxels()
+    assert np.array_equal(ko, kg) and np.array_equal(no, ng)
+    co6 = np.stack([co[:, 0, 0], co[:, 0, 1], co[:, 0, 2], co[:, 1, 1], co[:, 1, 2], co[:, 2, 2]], axis=1)
+    assert np.array_equal(mo[:, :3], mg) and np.array_equal(co6, cg)            # bit for bit
+    g.create_voxelmap()
+    k2, m2, c2, n2 = g.getVoxels()
+    assert np.array_equal(mg, m2) and np.array_equal(cg, c2)
+    runs = []
+    for _ in range(2):
+        r = RotVGICP(); r.setDeterministic(True)
+        if grid == "uniform":
+            r.setResolution(1.0)
+        else:
+            r.setPolarResolution(0.175, 0.175, 2.0)
+        r.setOptimizerType(capi.OPT_LM); r.setInputTarget(tgt); r.setInputSource(src)
+        r.align(); runs.append((r.getFinalPoseDouble().copy(), r.nrIterations(), r.getFinalHessian().copy()))
+    assert np.array_equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1] and np.array_equal(runs[0][2], runs[1][2])
+
+
 @pytest.mark.parametrize("grid,method", [("polar", capi.DIRECT1), ("polar", capi.DIRECT7), ("uniform", capi.DIRECT1),
                                          ("uniform", capi.DIRECT7), ("uniform", capi.DIRECT27)])
 def test_linearize_per_call(small_pair, grid, method):
