@@ -165,6 +165,10 @@ rg_ctx* rg_batch_ctx(rg_batch*, int pair);      /* per-pair context for setters 
 int  rg_batch_align(rg_batch*, const float* guesses /* n_pairs*16 or NULL */, float* final_transformations /* n_pairs*16 */);
 double rg_batch_last_linearize_us(const rg_batch*);   /* mean device time of the fused launches (CUDA events) */
 int    rg_batch_last_linearize_launches(const rg_batch*);
+/* stage times of the last rg_batch_align, CUDA events on the batch stream: out[0] covariance estimation (index build + search + epilogue, all
+ * groups) ms, out[1] of which the search kernels (chunk + fallback) ms, out[2] voxel maps ms, out[3] iterations ms (first launch to last result,
+ * host solves included), out[4] sum of the fused linearize kernels ms, out[5] points whose covariance was estimated, out[6] fused launches */
+int    rg_batch_last_stages(const rg_batch*, double out[8]);
 void*  rg_batch_stream(const rg_batch*);               /* cudaStream_t the batch launches on (for event timing) */
 void*  rg_stream(const rg_ctx*);                       /* cudaStream_t of a stand-alone context           */
 /* number of this library's own kernels launched so far in this process (library-internal kernels of

@@ -120,7 +120,7 @@ def load():
         "rg_batch_create": [i, i, C.POINTER(vp)], "rg_batch_destroy": [vp], "rg_batch_ctx": [vp, i],
         "rg_batch_align": [vp, fp, fp], "rg_batch_last_linearize_us": [vp], "rg_batch_last_linearize_launches": [vp],
         "rg_set_reduce_hook": [vp, REDUCE_FN, vp, i], "rg_set_source_shard": [vp, sz, sz], "rg_front_end_frame": [vp, vp, sz, vp, vp, i, vp, vp], "rg_cloud_info_serialize": [vp, i, vp, vp, vp, sz, vp], "rg_set_input_from_cloud_info": [vp, i, vp, sz, vp, vp], "rg_s2m_set_map": [vp, vp, sz, vp, sz, sz], "rg_s2m_set_scan": [vp, vp, sz, vp, sz, sz], "rg_s2m_linearize": [vp, vp, vp, vp, vp], "rg_s2m_get_coefficients": [vp, vp, vp, vp, vp], "rg_s2m_optimize": [vp, vp, i, i, i, vp], "rg_sc_make_and_save": [vp, vp, sz, sz, C.c_double], "rg_sc_size": [vp], "rg_sc_clear": [vp], "rg_sc_get": [vp, i, vp, vp, vp], "rg_sc_distance": [vp, i, i, vp, vp], "rg_sc_detect": [vp, vp, vp], "rg_get_fitness_score": [vp, vp, C.c_double, vp], "rg_nearest_target": [vp, vp, vp, vp], "rg_set_deskew": [vp, vp], "rg_shard_export": [vp, vp], "rg_shard_connect": [vp, i, i, vp], "rg_batch_stream": [vp], "rg_stream": [vp], "rg_kernel_launch_count": [],
-        "rg_set_deterministic": [vp, i], "rg_reset_voxelmap": [vp], "rg_set_target_shard": [vp, i, i], "rg_set_voxel_merge_hook": [vp, VOXEL_MERGE_FN, vp], "rg_voxel_import": [vp, vp, vp, i],
+        "rg_batch_last_stages": [vp, dp], "rg_set_deterministic": [vp, i], "rg_reset_voxelmap": [vp], "rg_set_target_shard": [vp, i, i], "rg_set_voxel_merge_hook": [vp, VOXEL_MERGE_FN, vp], "rg_voxel_import": [vp, vp, vp, i],
     }
     for name, args in protos.items():
         getattr(L, name).argtypes = args

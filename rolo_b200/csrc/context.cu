@@ -125,14 +125,21 @@ int upload_cloud(rg_ctx* c, Cloud& cl, const float* host, size_t n, size_t strid
     RG_CUDA(c, cudaEventRecord(c->ev_upload, c->stream));
     RG_CUDA(c, cudaStreamWaitEvent(us, c->ev_upload, 0));
   }
-  if (c->staging.cap < n * stride_bytes) RG_CUDA(c, cudaStreamSynchronize(us));   // about to re-allocate a buffer in-flight work may read
-  RG_CUDA(c, c->staging.ensure(c->device, n * stride_bytes));
   // pageable memory: the runtime stages the copy before returning; page-locked memory: truly asynchronous, the caller keeps
   // the cloud alive until the next solving call returns (pcl::Registration holds the cloud's shared_ptr, as in the reference)
-  RG_CUDA(c, cudaMemcpyAsync(c->staging.p, host, n * stride_bytes, cudaMemcpyHostToDevice, us));
-  g_launches++;
-  extract_points_kernel<<<(n_pad + 255) / 256, 256, 0, us>>>(c->staging.p, stride_bytes, (int)n, n_pad, cl.pts.p);
-  RG_CUDA(c, cudaGetLastError());
+  if (stride_bytes == sizeof(float4)) {
+    // 16-byte records (pcl::PointXYZ, float4): the copy engine writes the device layout directly — no staging buffer and no kernel
+    // that would have to squeeze in beside the persistent search kernels of an earlier group (no kernel reads the 4th component)
+    RG_CUDA(c, cudaMemcpyAsync(cl.pts.p, host, n * sizeof(float4), cudaMemcpyHostToDevice, us));
+    if ((size_t)n_pad > n) RG_CUDA(c, cudaMemsetAsync(cl.pts.p + n, 0, ((size_t)n_pad - n) * sizeof(float4), us));
+  } else {
+    if (c->staging.cap < n * stride_bytes) RG_CUDA(c, cudaStreamSynchronize(us));   // about to re-allocate a buffer in-flight work may read
+    RG_CUDA(c, c->staging.ensure(c->device, n * stride_bytes));
+    RG_CUDA(c, cudaMemcpyAsync(c->staging.p, host, n * stride_bytes, cudaMemcpyHostToDevice, us));
+    g_launches++;
+    extract_points_kernel<<<(n_pad + 255) / 256, 256, 0, us>>>(c->staging.p, stride_bytes, (int)n, n_pad, cl.pts.p);
+    RG_CUDA(c, cudaGetLastError());
+  }
   if (us != c->stream) {
     RG_CUDA(c, cudaEventRecord(c->ev_upload, us));
     // inside a batch the shared batch stream is NOT made to wait here: rg_batch_align joins the uploads group by group
@@ -166,7 +173,8 @@ int upload_cloud_device(rg_ctx* c, Cloud& cl, const float* dev, size_t n, cudaSt
 
 // RotVGICP::calculate_covariances (rot_vgicp_impl.hpp:421-496) of a GROUP of clouds (one launch chain for all of them) on `stream`,
 // with the scratch `bufs`. knn_out (optional, single cloud only) receives the unordered neighbour sets.
-int calc_cov_group(rg_ctx* c, const std::vector<Cloud*>& clouds, KnnBufs& bufs, cudaStream_t stream, int* knn_out = nullptr) {
+int calc_cov_group(rg_ctx* c, const std::vector<Cloud*>& clouds, KnnBufs& bufs, cudaStream_t stream, int* knn_out = nullptr,
+                   cudaEvent_t ev_knn0 = nullptr, cudaEvent_t ev_knn1 = nullptr) {
   if (clouds.empty()) return RG_OK;
   if (c->regularization_method < RG_REG_NONE || c->regularization_method > RG_REG_PLANE_S)
     return set_err(c, RG_ERR_UNSUPPORTED, "here must not be reached (unknown regularization method; reference abort()s, rot_vgicp_impl.hpp:472-474)");
@@ -218,6 +226,7 @@ int calc_cov_group(rg_ctx* c, const std::vector<Cloud*>& clouds, KnnBufs& bufs, 
   KnnGroup g;
   g.clouds = desc.data(); g.n_clouds = (int)desc.size(); g.total = (int)total; g.max_n = max_n; g.k = k; g.method = c->regularization_method;
   g.s = bufs.view();
+  g.ev_knn0 = ev_knn0; g.ev_knn1 = ev_knn1;
   static const bool want_stats = std::getenv("ROLO_KNN_STATS") != nullptr;   // development aid: work counters of the chunk kernel on stderr
   DevBuf<unsigned long long> stats;
   if (want_stats) { RG_CUDA(c, stats.ensure(c->device, 8)); RG_CUDA(c, cudaMemsetAsync(stats.p, 0, 64, stream)); g.stats = stats.p; }
@@ -1064,6 +1073,8 @@ void rg_batch_destroy(rg_batch* b) {
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->ev_inputs) cudaEventDestroy(b->ev_inputs);
+  for (auto e : b->ev_stage) if (e) cudaEventDestroy(e);
+  for (auto e : b->ev_knn) cudaEventDestroy(e);
   for (auto ev : b->setup_events) cudaEventDestroy(ev);
   for (auto st : b->setup_streams) { cudaStreamSynchronize(st); pool().stream_put(b->device, st); }
   delete b;
@@ -1072,6 +1083,7 @@ void rg_batch_destroy(rg_batch* b) {
 rg_ctx* rg_batch_ctx(rg_batch* b, int pair) { return (b && pair >= 0 && pair < (int)b->pairs.size()) ? b->pairs[pair] : nullptr; }
 double rg_batch_last_linearize_us(const rg_batch* b) { return (b && b->lin_launches) ? b->lin_us_sum / b->lin_launches : -1.0; }
 int rg_batch_last_linearize_launches(const rg_batch* b) { return b ? b->lin_launches : 0; }
+int rg_batch_last_stages(const rg_batch* b, double out[8]) { if (!b || !out) return RG_ERR_INVALID; for (int i = 0; i < 8; i++) out[i] = b->stage_ms[i]; return RG_OK; }
 void* rg_batch_stream(const rg_batch* b) { return b ? (void*)b->stream : nullptr; }
 void* rg_stream(const rg_ctx* c) { return c ? (void*)c->stream : nullptr; }
 unsigned long long rg_kernel_launch_count(void) { return g_launches.load(); }
@@ -1091,6 +1103,9 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
     c->voxel_ok = false; c->st_ok = false; c->have_corr = false;
   }
   const int GROUP_PAIRS = 32;
+  for (auto& e : b->ev_stage) if (!e) cudaEventCreate(&e);
+  b->knn_groups = 0; b->knn_queries = 0;
+  cudaEventRecord(b->ev_stage[0], b->stream);
   for (int g0 = 0; g0 < P; g0 += GROUP_PAIRS) {
     const int g1 = std::min(P, g0 + GROUP_PAIRS);
     std::vector<char> done(g1 - g0, 0);
@@ -1109,9 +1124,14 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
         if (!c->tgt.has_cov) todo.push_back(&c->tgt);
         if (!c->src.has_cov) todo.push_back(&c->src);
       }
-      if (int rc = calc_cov_group(lead, todo, b->knn, b->stream)) return rc;
+      if (todo.empty()) continue;
+      while ((int)b->ev_knn.size() < 2 * (b->knn_groups + 1)) { cudaEvent_t e = nullptr; cudaEventCreate(&e); b->ev_knn.push_back(e); }
+      if (int rc = calc_cov_group(lead, todo, b->knn, b->stream, nullptr, b->ev_knn[2 * b->knn_groups], b->ev_knn[2 * b->knn_groups + 1])) return rc;
+      if (lead->k_correspondences <= 32) b->knn_groups++;
+      for (Cloud* cl : todo) b->knn_queries += cl->n;
     }
   }
+  cudaEventRecord(b->ev_stage[1], b->stream);
   // stage 2: every voxel map by one launch chain
   {
     std::vector<VoxelBuild> builds(P);
@@ -1121,6 +1141,7 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
     g_launches += 4;
     for (int i = 0; i < P; i++) { rg_ctx* c = b->pairs[i]; c->voxel_ok = true; c->n_vox = -1; c->st_ok = false; c->have_corr = false; }
   }
+  cudaEventRecord(b->ev_stage[2], b->stream);
   for (int i = 0; i < P; i++) {
     rg_ctx* c = b->pairs[i];
     if (int rc = prepare_linearize(c)) return rc;
@@ -1200,6 +1221,16 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
         }
       }
     }
+  }
+  cudaEventRecord(b->ev_stage[3], b->stream);
+  if (cudaEventSynchronize(b->ev_stage[3]) == cudaSuccess) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, b->ev_stage[0], b->ev_stage[1]); b->stage_ms[0] = ms;
+    double knn = 0; for (int g = 0; g < b->knn_groups; g++) { cudaEventElapsedTime(&ms, b->ev_knn[2 * g], b->ev_knn[2 * g + 1]); knn += ms; }
+    b->stage_ms[1] = knn;
+    cudaEventElapsedTime(&ms, b->ev_stage[1], b->ev_stage[2]); b->stage_ms[2] = ms;
+    cudaEventElapsedTime(&ms, b->ev_stage[2], b->ev_stage[3]); b->stage_ms[3] = ms;
+    b->stage_ms[4] = b->lin_us_sum * 1e-3; b->stage_ms[5] = b->knn_queries; b->stage_ms[6] = b->lin_launches;
   }
   int rc_all = RG_OK;
   {   // voxel-key range / table overflow flags of all pairs: P small async copies, one sync

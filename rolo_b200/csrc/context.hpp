@@ -300,6 +300,10 @@ struct rg_batch {
   cudaEvent_t ev_inputs = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   double lin_us_sum = 0; int lin_launches = 0;
+  // stage timing of the last rg_batch_align (CUDA events on the batch stream)
+  cudaEvent_t ev_stage[4] = {nullptr, nullptr, nullptr, nullptr};   // start, covariances done, voxel maps done, iterations done
+  std::vector<cudaEvent_t> ev_knn;                                    // pairs around the search kernels of every covariance group
+  int knn_groups = 0; double knn_queries = 0; double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   std::string err;
 };
 

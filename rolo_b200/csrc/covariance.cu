@@ -1180,6 +1180,7 @@ cudaError_t launch_covariances_group(const KnnGroup& g, cudaStream_t stream, int
   gather_sorted_kernel<<<dim3(nb, nc), tb, 0, stream>>>(ref, g.s.idx_b, g.s.codes_b, g.s.sorted, g.s.codes_a);
   bucket_table_kernel<<<dim3((N_BUCKETS + 1 + tb - 1) / tb, nc), tb, 0, stream>>>(ref, g.s.codes_a, g.s.bucket_start);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if (g.ev_knn0) cudaEventRecord(g.ev_knn0, stream);
   int total_chunks = 0;
   for (int c = 0; c < g.n_clouds; c++) total_chunks += knn_owned_chunks(g.clouds[c].n, g.clouds[c].shard_rank, g.clouds[c].shard_world);   // == the chunk_off prefix the caller filled in
   if (g.k <= 8) e = launch_chunk<8>(g, total_chunks, stream);
@@ -1190,6 +1191,7 @@ cudaError_t launch_covariances_group(const KnnGroup& g, cudaStream_t stream, int
   else e = launch_chunk<32>(g, total_chunks, stream);
   if (e != cudaSuccess) return e;
   knn_fallback_kernel<<<296, 256, 0, stream>>>(g.s.clouds, g.s.sorted, g.s.codes_a, g.s.bucket_start, g.s.bbox, g.s.fail, g.k, g.method);
+  if (g.ev_knn1) cudaEventRecord(g.ev_knn1, stream);
   if (own_launches) *own_launches = 7;   // bbox_init, bbox, morton, gather, bucket table, chunk kNN + covariance, fallback (+ 1 memset not counted; cub's kernels not counted)
   return cudaGetLastError();
 }

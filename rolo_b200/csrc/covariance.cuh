@@ -58,6 +58,7 @@ struct KnnGroup {
   int method;                 // RG_REG_*
   KnnScratch s;
   unsigned long long* stats = nullptr;   // optional device counters [8] (development: ROLO_KNN_STATS=1)
+  cudaEvent_t ev_knn0 = nullptr, ev_knn1 = nullptr;   // optional: recorded around the search kernels (chunk + fallback) for stage timing
 };
 constexpr int KNN_MAX_CLOUDS = 4096;
 constexpr int KNN_SHARD_BLOCK = 2048;   // points per dealt block of a sharded query set (64 chunks of 32)

@@ -369,5 +369,12 @@ class RotVGICPBatch:
         return out
 
     def stream(self): return self._L.rg_batch_stream(self._h)
+
+    def lastStages(self) -> dict:
+        """Stage times (ms) of the last align(): CUDA events on the batch stream."""
+        out = np.zeros(8)
+        capi.check(self._L.rg_batch_last_stages(self._h, out.ctypes.data_as(capi.dp)))
+        return {"covariances_ms": out[0], "knn_kernels_ms": out[1], "voxel_maps_ms": out[2], "iterations_ms": out[3], "linearize_kernels_ms": out[4],
+                "covariance_points": int(out[5]), "linearize_launches": int(out[6])}
     def lastLinearizeUs(self): return self._L.rg_batch_last_linearize_us(self._h)
     def lastLinearizeLaunches(self): return self._L.rg_batch_last_linearize_launches(self._h)
