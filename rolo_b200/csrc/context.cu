@@ -111,7 +111,9 @@ GridParams make_grid(const rg_ctx* c) {
 }
 
 int upload_cloud(rg_ctx* c, Cloud& cl, const float* host, size_t n, size_t stride_bytes) {
-  if (use_device(c)) return RG_ERR_CUDA;
+  // no lazy join here (use_device would order the shared batch stream after this pair's previous upload: the source upload after the
+  // target upload of every pair, i.e. the batch stream after nearly all copies — the overlap of copies and kernels would be gone)
+  { cudaError_t e = cudaSetDevice(c->device); if (e != cudaSuccess) return set_err(c, RG_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)); }
   if (n > 0 && !host) return set_err(c, RG_ERR_INVALID, "null cloud pointer");
   if (n > 0 && (stride_bytes < 12 || stride_bytes % 4)) return set_err(c, RG_ERR_INVALID, "stride_bytes must be a multiple of 4 and >= 12");
   if (n > (size_t)1 << 30) return set_err(c, RG_ERR_INVALID, "cloud too large");
@@ -1048,7 +1050,7 @@ int rg_batch_create(int device, int n_pairs, rg_batch** out) {
   std::memset(b->flag_host, 0, sizeof(unsigned) * n_pairs);
   cudaEventCreate(&b->ev0); cudaEventCreate(&b->ev1);
   cudaEventCreateWithFlags(&b->ev_inputs, cudaEventDisableTiming);
-  const int n_setup = std::min(n_pairs, 4);
+  const int n_setup = 1;   // ONE upload stream: the copy engine then serves the pairs strictly in issue order, so the first covariance group's inputs land first
   for (int i = 0; i < n_setup; i++) {
     cudaStream_t st = nullptr; cudaEvent_t ev = nullptr;
     if (pool().stream_get(b->device, &st) != cudaSuccess || cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
