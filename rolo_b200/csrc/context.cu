@@ -367,33 +367,29 @@ int sm_count(int device) {
 int lin_slots(int device) { return sm_count(device) * 2; }   // 2 resident CTAs per SM (launch bounds of the fused kernel)
 
 // make sure the static descriptor + scratch for the fused kernel exist
-int prepare_linearize(rg_ctx* c) {
+// make sure the static descriptor + scratch for the fused kernel exist. Inside rg_batch_align (`batch_out` != null) only the
+// descriptor is produced — the batch uploads all of them with one copy and builds its own persistent-CTA schedule; the stand-alone
+// launch shape (own schedule + descriptor on the device, two synchronising copies) is then set up lazily, if the pair is ever
+// evaluated on its own.
+int prepare_linearize(rg_ctx* c, LinStatic* batch_out = nullptr) {
   if (use_device(c)) return RG_ERR_CUDA;
   if (int rc = check_grid(c)) return rc;
   if (c->src.n == 0) return set_err(c, RG_ERR_INVALID, "no source cloud");
   if (!c->src.has_cov) return set_err(c, RG_ERR_INVALID, "source covariances missing");
   if (!c->voxel_ok) { if (int rc = build_voxelmap(c)) return rc; }   // lazily, as rot_vgicp_impl.hpp:227-230
   const int noff = noff_of(c->search_method);
-  if (c->st_ok && c->corr_noff == noff) return RG_OK;
-  const int n_pairs = c->batch ? (int)c->batch->pairs.size() : 1;
+  if (c->st_ok && c->corr_noff == noff && !batch_out && c->st_standalone_ok) return RG_OK;
   const int lo = (c->shard_hi > c->shard_lo) ? c->shard_lo : 0;
   const int n_eval = (c->shard_hi > c->shard_lo) ? (c->shard_hi - c->shard_lo) : c->src.n;
-  (void)n_pairs;
-  {   // stand-alone launch shape: one pair, persistent CTAs
-    std::vector<int> sched;
-    const int ntiles = (n_eval + TILE_PTS - 1) / TILE_PTS;
-    c->lin_grid = std::max(1, std::min(ntiles, lin_slots(c->device)));
-    build_schedule(&n_eval, 1, c->lin_grid, sched, c->lin_tiles);
-    RG_CUDA(c, c->sched_dev.ensure(c->device, sched.size()));
-    RG_CUDA(c, cudaMemcpyAsync(c->sched_dev.p, sched.data(), sched.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    RG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (!(c->st_ok && c->corr_noff == noff)) {
+    RG_CUDA(c, c->corr.ensure(c->device, (size_t)n_eval * noff));
+    c->corr_noff = noff; c->have_corr = false;
+    RG_CUDA(c, c->partials.ensure(c->device, (size_t)lin_slots(c->device) * RES_N));   // any launch grid fits
+    if (!c->counter.p) { RG_CUDA(c, c->counter.ensure(c->device, 4)); RG_CUDA(c, cudaMemsetAsync(c->counter.p, 0, 4 * sizeof(unsigned), c->stream)); }
+    RG_CUDA(c, c->result_dev.ensure(c->device, RES_N));
+    RG_CUDA(c, c->st_dev.ensure(c->device, 1));
+    c->st_standalone_ok = false;
   }
-  RG_CUDA(c, c->corr.ensure(c->device, (size_t)n_eval * noff));
-  c->corr_noff = noff; c->have_corr = false;
-  RG_CUDA(c, c->partials.ensure(c->device, (size_t)lin_slots(c->device) * RES_N));   // any launch grid fits
-  if (!c->counter.p) { RG_CUDA(c, c->counter.ensure(c->device, 4)); RG_CUDA(c, cudaMemsetAsync(c->counter.p, 0, 4 * sizeof(unsigned), c->stream)); }
-  RG_CUDA(c, c->result_dev.ensure(c->device, RES_N));
-  RG_CUDA(c, c->st_dev.ensure(c->device, 1));
   if (!c->batch) {
     if (!c->result_host) {
       void* p = nullptr;
@@ -414,10 +410,20 @@ int prepare_linearize(rg_ctx* c) {
   st.grid = make_grid(c);
   st.shard_rank = c->p2p_rank; st.shard_world = (c->p2p_world > 1 && !c->batch) ? c->p2p_world : 0;
   for (int p = 0; p < XCHG_MAX_RANKS; p++) st.peer_xchg[p] = c->peer_xchg[p];
-  RG_CUDA(c, cudaMemcpyAsync(c->st_dev.p, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
-  if (c->batch) RG_CUDA(c, cudaMemcpyAsync(c->batch->st_dev.p + c->batch_index, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
-  RG_CUDA(c, cudaStreamSynchronize(c->stream));   // `st` is a stack object
   c->st_ok = true;
+  if (batch_out) { *batch_out = st; return RG_OK; }
+  {   // stand-alone launch shape: one pair, persistent CTAs
+    std::vector<int> sched;
+    const int ntiles = (n_eval + TILE_PTS - 1) / TILE_PTS;
+    c->lin_grid = std::max(1, std::min(ntiles, lin_slots(c->device)));
+    build_schedule(&n_eval, 1, c->lin_grid, sched, c->lin_tiles);
+    RG_CUDA(c, c->sched_dev.ensure(c->device, sched.size()));
+    RG_CUDA(c, cudaMemcpyAsync(c->sched_dev.p, sched.data(), sched.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    RG_CUDA(c, cudaMemcpyAsync(c->st_dev.p, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+    if (c->batch) RG_CUDA(c, cudaMemcpyAsync(c->batch->st_dev.p + c->batch_index, &st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+    RG_CUDA(c, cudaStreamSynchronize(c->stream));   // `st` and `sched` are stack objects
+  }
+  c->st_standalone_ok = true;
   return RG_OK;
 }
 
@@ -1144,9 +1150,10 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
     for (int i = 0; i < P; i++) { rg_ctx* c = b->pairs[i]; c->voxel_ok = true; c->n_vox = -1; c->st_ok = false; c->have_corr = false; }
   }
   cudaEventRecord(b->ev_stage[2], b->stream);
+  std::vector<LinStatic> st_host(P);
   for (int i = 0; i < P; i++) {
     rg_ctx* c = b->pairs[i];
-    if (int rc = prepare_linearize(c)) return rc;
+    if (int rc = prepare_linearize(c, &st_host[i])) return rc;
     if (noff < 0) noff = c->corr_noff;
     if (c->corr_noff != noff) return set_err(c, RG_ERR_INVALID, "batch align: all pairs must use the same neighbor search method");
     double g[16];
@@ -1157,9 +1164,7 @@ int rg_batch_align(rg_batch* b, const float* guesses, float* out_T) {
   b->sched_group.clear();   // cloud sizes may have changed since the last call
   std::vector<host::Request> req(P);
   std::vector<int> group;
-  std::vector<LinStatic> st_host(P);
-  RG_CUDA(nullptr, cudaMemcpyAsync(st_host.data(), b->st_dev.p, sizeof(LinStatic) * P, cudaMemcpyDeviceToHost, b->stream));
-  RG_CUDA(nullptr, cudaStreamSynchronize(b->stream));
+  RG_CUDA(nullptr, cudaMemcpyAsync(b->st_dev.p, st_host.data(), sizeof(LinStatic) * P, cudaMemcpyHostToDevice, b->stream));   // pageable: staged before the call returns
   for (;;) {
     // collect the pending request of every unfinished pair and serve them grouped by kernel variant
     std::vector<int> pend;

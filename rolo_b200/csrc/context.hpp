@@ -219,6 +219,7 @@ struct rg_ctx {
   DevBuf<unsigned> counter;
   DevBuf<double> result_dev;
   DevBuf<LinStatic> st_dev; bool st_ok = false;
+  bool st_standalone_ok = false;        // own schedule + descriptor uploaded (stand-alone launches); a batch skips it
   double* result_host = nullptr;        // mapped pinned [RES_N] (owned; stand-alone contexts)
   unsigned* flag_host = nullptr;        // mapped pinned
   double* result_view = nullptr;        // where the kernel writes this pair's result (own block or the batch's)
