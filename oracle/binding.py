@@ -403,6 +403,7 @@ class SCManager:
 
 _REF_SC_PATH = os.path.join(_HERE, "_ref", "librolo_ref_sc.so")
 _REF_FE_PATH = os.path.join(_HERE, "_ref", "librolo_ref_fe.so")
+_REF_BM_PATH = os.path.join(_HERE, "_ref", "librolo_ref_bm.so")
 
 
 def ref_sc_available() -> bool:
@@ -623,6 +624,63 @@ def ref_feature_extraction(proj: dict, n_scan, horizon, edge_threshold=0.8, surf
     L.rfe_feature_extraction(vp(ext), vp(col), vp(rng), vp(st), vp(en), C.c_int(n), C.c_int(n_scan), C.c_int(horizon), C.c_float(edge_threshold),
                              C.c_float(surf_threshold), C.c_float(surf_leaf_size), vp(curv), vp(picked), vp(label), vp(corner), C.byref(nc), vp(surf), C.byref(ns))
     return {"curvature": curv, "neighbor_picked": picked, "label": label, "corner": corner[:nc.value].copy(), "surface": surf[:ns.value].copy()}
+
+def ref_bm_available() -> bool:
+    return os.path.exists(_REF_BM_PATH)
+
+
+class RefScan2Map:
+    """The REFERENCE's own scan-to-map member functions (cornerOptimization, surfOptimization, combineOptimizationCoeffs, LMOptimization,
+    scan2MapOptimization of src/backMapping.cpp, compiled into oracle/_ref/librolo_ref_bm.so by oracle/ref_bm_driver.cpp). Same
+    interface as Scan2Map where the two overlap."""
+
+    def __init__(self, threads: int = 4):
+        self.L = C.CDLL(_REF_BM_PATH)
+        self.L.rbm_create.restype = C.c_void_p
+        self.h = C.c_void_p(self.L.rbm_create())
+        self.L.rbm_set_num_threads(self.h, threads)
+        self.n_corner = self.n_surf = 0
+
+    def __del__(self):
+        try:
+            self.L.rbm_destroy(self.h)
+        except Exception:
+            pass
+
+    def setMap(self, corner, surf):
+        c, cp, cn, cs = Scan2Map._c(corner); s, sp, sn, ss = Scan2Map._c(surf)
+        assert cs == ss
+        self.L.rbm_set_map(self.h, cp, cn, sp, sn, C.c_size_t(cs))
+
+    def setScan(self, corner, surf):
+        c, cp, cn, cs = Scan2Map._c(corner); s, sp, sn, ss = Scan2Map._c(surf)
+        assert cs == ss
+        self.n_corner, self.n_surf = c.shape[0], s.shape[0]
+        self.L.rbm_set_scan(self.h, cp, cn, sp, sn, C.c_size_t(cs))
+
+    def associate(self, tf6):
+        """cornerOptimization + surfOptimization + combineOptimizationCoeffs at the pose: flags, coefficients, laserCloudSelNum."""
+        tf = np.ascontiguousarray(tf6, dtype=np.float32)
+        cc = np.empty((self.n_corner, 4), np.float32); fc = np.empty(self.n_corner, np.uint8)
+        cs = np.empty((self.n_surf, 4), np.float32); fs = np.empty(self.n_surf, np.uint8)
+        vp = lambda a: C.c_void_p(a.ctypes.data)
+        n = self.L.rbm_associate(self.h, vp(tf), vp(cc), vp(fc), vp(cs), vp(fs))
+        return {"n_sel": n, "coeff_corner": cc, "flag_corner": fc, "coeff_surf": cs, "flag_surf": fs}
+
+    def step(self, tf6, iter_count: int):
+        """one pass of the loop body of scan2MapOptimization at the pose: returns the updated pose, LMOptimization's result, isDegenerate."""
+        tf = np.array(tf6, dtype=np.float32)
+        deg, sel = C.c_int(), C.c_int()
+        conv = self.L.rbm_step(self.h, C.c_void_p(tf.ctypes.data), iter_count, C.byref(deg), C.byref(sel))
+        return {"pose": tf, "converged": bool(conv), "degenerate": bool(deg.value), "n_sel": sel.value}
+
+    def optimize(self, tf6, edge_min=10, surf_min=100):
+        """scan2MapOptimization() itself (30 iterations at most)."""
+        tf = np.array(tf6, dtype=np.float32)
+        deg = C.c_int()
+        rc = self.L.rbm_scan2map(self.h, C.c_void_p(tf.ctypes.data), edge_min, surf_min, C.byref(deg))
+        return {"pose": tf, "enough_features": rc == 0, "degenerate": bool(deg.value)}
+
 
 def require_ref(available, what: str):
     """Module-level guard of the tests that pin the oracle to oracle/_ref: where the reference checkout exists the library is built

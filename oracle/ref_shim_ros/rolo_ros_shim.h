@@ -161,5 +161,7 @@ struct Mat {
   Mat(int r, int c, int /*type: CV_32F*/, const Scalar& s) : rows(r), cols(c), d((size_t)r * c, (float)s.v[0]) {}
   template <typename T> T& at(int r, int c) { static_assert(std::is_same<T, float>::value, "CV_32F only"); return d[(size_t)r * cols + c]; }
   template <typename T> const T& at(int r, int c) const { return d[(size_t)r * cols + c]; }
+  void copyTo(Mat& o) const { o = *this; }              // deep copy; this stand-in has value semantics throughout
+  Mat inv() const;                                       // defined in ref_shim_bm/cv_ops.hpp (only the scan-to-map driver needs it)
 };
 }  // namespace cv

@@ -10,15 +10,17 @@
  * All arithmetic is float like the reference's (PointType = pcl::PointXYZI, cv::Mat CV_32F); AtA/AtB are accumulated in
  * double and rounded to float (cv::gemm's working type for CV_32F is double).
  *
- * PINNING (partial): the reference has no test or golden vector for this path and backMapping.cpp cannot be compiled here
- * (ROS, GTSAM, PCL, OpenCV C++ are absent), so the path as a whole is PARITY UNPINNED. Its third-party numerics are pinned
- * where the real library exists in the image: the restated cv::eigen (3x3 and 6x6) and cv::Mat::inv are BIT-EQUAL to OpenCV
- * 4.13 (python cv2; golden vectors tests/golden/opencv_s2m_golden.npz from tools/make_opencv_golden.py, plus a live check);
- * cv::solve(DECOMP_QR) agrees to rounding only (that build dispatches to LAPACK). Still restated from their published
- * algorithms: pcl::getTransformation's closed form (checked against scipy), exact kNN under (float distance, index) order,
- * Eigen::colPivHouseholderQr (checked against numpy lstsq), cv::gemm's double accumulation. The transcription of the
- * reference's own formulas (coefficients, LOAM Jacobian) is checked against their geometric meaning and finite differences
- * in tests/test_scan2map_cpu.py. Compiled with -ffp-contract=off.
+ * PINNING: PINNED to the reference's own code. backMapping.cpp cannot be compiled as a file here (roscpp, tf, GTSAM, small_gicp, PCL I/O
+ * are absent), but the member functions above can: oracle/extract_ref_members.py takes their text from the reference file where it lies
+ * at build time, oracle/ref_bm_driver.cpp compiles them unmodified (with the reference's include/rolo/utility.h in front) into
+ * oracle/_ref/librolo_ref_bm.so, and tests/test_scan2map_vs_ref_cpu.py requires this restatement to be BIT-EQUAL to them: selection
+ * flags and coefficients per point, every Gauss-Newton pass, the degeneracy projection, the convergence test, the whole
+ * scan2MapOptimization trajectory. Both sides share the restated third-party numerics (oracle/s2m_numerics.hpp) and the exact kd-tree;
+ * those are pinned where the real library exists in the image: cv::eigen (3x3 and 6x6) and cv::Mat::inv are BIT-EQUAL to OpenCV 4.13
+ * (python cv2; golden vectors tests/golden/opencv_s2m_golden.npz from tools/make_opencv_golden.py, plus a live check);
+ * cv::solve(DECOMP_QR) agrees to rounding only (that build dispatches to LAPACK). Restated from their published algorithms without a
+ * real library to compare with: pcl::getTransformation's closed form (checked against scipy), exact kNN under (float distance, index)
+ * order, Eigen::colPivHouseholderQr (checked against numpy lstsq), cv::gemm's double accumulation. Compiled with -ffp-contract=off.
  */
 #include <omp.h>
 
@@ -28,8 +30,10 @@
 #include <vector>
 
 #include "kdtree.hpp"
+#include "s2m_numerics.hpp"
 
 namespace {
+using namespace s2m_num;
 
 // pcl::getTransformation(x, y, z, roll, pitch, yaw) (pcl/common/impl/eigen.hpp), rows of the 3x4 float matrix
 void get_transformation(const float tf[6], float t[12]) {
@@ -39,135 +43,6 @@ void get_transformation(const float tf[6], float t[12]) {
   t[0] = A * C; t[1] = A * DF - B * E; t[2] = B * F + A * DE; t[3] = tf[3];
   t[4] = B * C; t[5] = A * E + B * DF; t[6] = B * DE - A * F; t[7] = tf[4];
   t[8] = -D;    t[9] = C * F;          t[10] = C * E;         t[11] = tf[5];
-}
-
-inline float hyp(float a, float b) {   // OpenCV's hypot helper
-  a = std::fabs(a); b = std::fabs(b);
-  if (a > b) { b /= a; return a * std::sqrt(1 + b * b); }
-  if (b > 0) { a /= b; return b * std::sqrt(1 + a * a); }
-  return 0;
-}
-
-// cv::eigen for a symmetric CV_32F matrix (JacobiImpl_): classical Jacobi choosing the largest off-diagonal pivot, rows of V
-// are the eigenvectors, eigenvalues sorted descending. A (n x n, row-major) is destroyed.
-void jacobi_eigen(int n, float* A, float* W, float* V) {
-  const float eps = 1.1920929e-07f;
-  std::vector<int> indR(n), indC(n);
-  for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) V[i * n + j] = 0.f; V[i * n + i] = 1.f; }
-  for (int k = 0; k < n; k++) {
-    W[k] = A[k * n + k];
-    if (k < n - 1) { int m = k + 1; float mv = std::fabs(A[k * n + m]); for (int i = k + 2; i < n; i++) { float v = std::fabs(A[k * n + i]); if (mv < v) { mv = v; m = i; } } indR[k] = m; }
-    if (k > 0) { int m = 0; float mv = std::fabs(A[k]); for (int i = 1; i < k; i++) { float v = std::fabs(A[i * n + k]); if (mv < v) { mv = v; m = i; } } indC[k] = m; }
-  }
-  if (n > 1) for (int iters = 0, maxIters = n * n * 30; iters < maxIters; iters++) {
-    int k = 0, l; float mv = std::fabs(A[indR[0]]);
-    for (int i = 1; i < n - 1; i++) { float v = std::fabs(A[i * n + indR[i]]); if (mv < v) { mv = v; k = i; } }
-    l = indR[k];
-    for (int i = 1; i < n; i++) { float v = std::fabs(A[indC[i] * n + i]); if (mv < v) { mv = v; k = indC[i]; l = i; } }
-    float p = A[k * n + l];
-    if (std::fabs(p) <= eps) break;
-    float y = (W[l] - W[k]) * 0.5f;
-    float t = std::fabs(y) + hyp(p, y);
-    float s = hyp(p, t);
-    float c = t / s;
-    s = p / s; t = (p / t) * p;
-    if (y < 0) { s = -s; t = -t; }
-    A[k * n + l] = 0;
-    W[k] -= t; W[l] += t;
-    float a0, b0;
-#define ROT(v0, v1) a0 = v0, b0 = v1, v0 = a0 * c - b0 * s, v1 = a0 * s + b0 * c
-    for (int i = 0; i < k; i++) ROT(A[i * n + k], A[i * n + l]);
-    for (int i = k + 1; i < l; i++) ROT(A[k * n + i], A[i * n + l]);
-    for (int i = l + 1; i < n; i++) ROT(A[k * n + i], A[l * n + i]);
-    for (int i = 0; i < n; i++) ROT(V[k * n + i], V[l * n + i]);
-#undef ROT
-    for (int j = 0; j < 2; j++) {
-      int idx = j == 0 ? k : l;
-      if (idx < n - 1) { int m = idx + 1; float mv2 = std::fabs(A[idx * n + m]); for (int i = idx + 2; i < n; i++) { float v = std::fabs(A[idx * n + i]); if (mv2 < v) { mv2 = v; m = i; } } indR[idx] = m; }
-      if (idx > 0) { int m = 0; float mv2 = std::fabs(A[idx]); for (int i = 1; i < idx; i++) { float v = std::fabs(A[i * n + idx]); if (mv2 < v) { mv2 = v; m = i; } } indC[idx] = m; }
-    }
-  }
-  for (int k = 0; k < n - 1; k++) {       // descending
-    int m = k;
-    for (int i = k + 1; i < n; i++) if (W[m] < W[i]) m = i;
-    if (k != m) { std::swap(W[m], W[k]); for (int i = 0; i < n; i++) std::swap(V[m * n + i], V[k * n + i]); }
-  }
-}
-
-// Householder reflector of x[0..m) (Eigen makeHouseholderInPlace): x[0] <- beta, x[1..] <- essential part, returns tau
-float householder(float* x, int m, int stride) {
-  float tail = 0.f;
-  for (int i = 1; i < m; i++) tail += x[i * stride] * x[i * stride];
-  const float c0 = x[0];
-  if (tail <= 1.17549435e-38f) { for (int i = 1; i < m; i++) x[i * stride] = 0.f; return 0.f; }
-  float beta = std::sqrt(c0 * c0 + tail);
-  if (c0 >= 0.f) beta = -beta;
-  for (int i = 1; i < m; i++) x[i * stride] = x[i * stride] / (c0 - beta);
-  x[0] = beta;
-  return (beta - c0) / beta;
-}
-
-// least squares min |A x - b| by Householder QR, optional column pivoting (rows x cols, row-major, A and b destroyed).
-// pivot = true: Eigen::ColPivHouseholderQR::solve (the 5x3 plane fit); false: cv::solve(DECOMP_QR) (the 6x6 normal equations)
-void qr_solve(int rows, int cols, float* A, float* b, float* x, bool pivot) {
-  std::vector<int> perm(cols);
-  std::vector<float> cn(cols);
-  for (int j = 0; j < cols; j++) { perm[j] = j; float s = 0.f; for (int i = 0; i < rows; i++) s += A[i * cols + j] * A[i * cols + j]; cn[j] = s; }
-  for (int k = 0; k < cols; k++) {
-    if (pivot) {
-      int m = k; float best = 0.f;
-      for (int j = k; j < cols; j++) { float s = 0.f; for (int i = k; i < rows; i++) s += A[i * cols + j] * A[i * cols + j]; cn[j] = s; if (j == k || s > best) { best = s; m = j; } }
-      if (m != k) { for (int i = 0; i < rows; i++) std::swap(A[i * cols + k], A[i * cols + m]); std::swap(perm[k], perm[m]); }
-    }
-    const float tau = householder(&A[k * cols + k], rows - k, cols);
-    if (tau != 0.f) {
-      for (int j = k + 1; j < cols; j++) {     // apply H = I - tau v v^T (v = [1, essential]) to the remaining columns
-        float dot = A[k * cols + j];
-        for (int i = k + 1; i < rows; i++) dot += A[i * cols + k] * A[i * cols + j];
-        dot *= tau;
-        A[k * cols + j] -= dot;
-        for (int i = k + 1; i < rows; i++) A[i * cols + j] -= dot * A[i * cols + k];
-      }
-      float dot = b[k];
-      for (int i = k + 1; i < rows; i++) dot += A[i * cols + k] * b[i];
-      dot *= tau;
-      b[k] -= dot;
-      for (int i = k + 1; i < rows; i++) b[i] -= dot * A[i * cols + k];
-    }
-  }
-  std::vector<float> y(cols);
-  for (int k = cols - 1; k >= 0; k--) {      // R y = (Q^T b)[0..cols)
-    float s = b[k];
-    for (int j = k + 1; j < cols; j++) s -= A[k * cols + j] * y[j];
-    const float d = A[k * cols + k];
-    y[k] = d != 0.f ? s / d : 0.f;
-  }
-  for (int k = 0; k < cols; k++) x[perm[k]] = y[k];
-}
-
-// cv::Mat::inv() (DECOMP_LU): Gauss-Jordan elimination with partial pivoting on [A | I]; returns false when singular
-bool invert_lu(int n, const float* Ain, float* inv) {
-  std::vector<float> A(Ain, Ain + n * n);
-  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) inv[i * n + j] = i == j ? 1.f : 0.f;
-  for (int i = 0; i < n; i++) {
-    int k = i;
-    for (int j = i + 1; j < n; j++) if (std::fabs(A[j * n + i]) > std::fabs(A[k * n + i])) k = j;
-    if (std::fabs(A[k * n + i]) < 1.1920929e-07f * 100) return false;
-    if (k != i) for (int j = 0; j < n; j++) { std::swap(A[i * n + j], A[k * n + j]); std::swap(inv[i * n + j], inv[k * n + j]); }
-    const float d = -1.f / A[i * n + i];
-    for (int j = i + 1; j < n; j++) {
-      const float alpha = A[j * n + i] * d;
-      for (int c = i + 1; c < n; c++) A[j * n + c] += alpha * A[i * n + c];
-      for (int c = 0; c < n; c++) inv[j * n + c] += alpha * inv[i * n + c];
-    }
-  }
-  for (int i = n - 1; i >= 0; i--)
-    for (int c = 0; c < n; c++) {
-      float s = inv[i * n + c];
-      for (int k = i + 1; k < n; k++) s -= A[i * n + k] * inv[k * n + c];
-      inv[i * n + c] = s / A[i * n + i];
-    }
-  return true;
 }
 
 struct S2M {
