@@ -663,127 +663,117 @@ __device__ __forceinline__ void knn_warp_merge(unsigned long long& top, unsigned
   }
 }
 
-// Level search: the 3x3x3 block of octree cells around the query is scanned at a level guessed from the Morton neighbours; the result is
-// exact once the k-th distance is inside the radius the block provably covers, else the block is taken one level coarser and scanned
-// again. Needs no a-priori bound: used when the Morton window gives a uselessly loose one.
-constexpr int KNN_BOX_CAP = 6144;     // fallback: box pass when the window bound's covering cells hold at most this many points, else the level search
-constexpr int KNN_CAND_CAP = 1024;    // prefer a finer level when the block holds more candidates than this
+// Descent: the cells that cover the ball's box are refined where it pays. Work items (a cell = one range of the sorted array) live on a
+// per-warp stack, nearest cell on top; a popped cell farther from the query than the current k-th distance is dropped, a small one is
+// scanned (32 candidates per step into the top-32), a large one is split into its 8 children (7 binary searches inside its range, one
+// per lane), which are pushed farthest first. The k-th distance shrinks as the near cells are scanned, so a stray point beside a dense
+// surface touches the few hundred candidates around its neighbours instead of the thousands inside its first box.
+constexpr int KNN_DESC_STACK = 160;   // 32 covering cells + 7 per level of refinement (13 levels)
+constexpr int KNN_DESC_LEAF = 128;    // cells up to this size are scanned, larger ones split
+constexpr int KNN_DESC_SPLITS = 4096; // splits per query before the descent stops refining (a guard, never reached on real clouds)
+constexpr int KNN_DESC_MIN = 512;     // covering cells holding at most this many points are scanned directly (no stack)
 
-__device__ unsigned long long knn_warp_query_levels(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes,
-                                             const int* __restrict__ bucket_start, int n, int k, const Quant& qn, int j, const float4 q) {
+struct DescItem { int lo, cnt; unsigned long long cell; };   // cell = cx | cy << 13 | cz << 26 | shift << 39
+
+// squared distance from the query (rel = q - bbox min, double) to the cell, a lower bound: the cell is widened by a slack that covers the
+// rounding of quantize()
+__device__ __forceinline__ double cell_min_d2(const Quant& qn, const double rel[3], unsigned cx, unsigned cy, unsigned cz, int sh) {
+  const double sz = qn.cell * (double)(1u << sh), slack = qn.cell * 1e-6;
+  const unsigned cc[3] = {cx, cy, cz};
+  double d2 = 0.0;
+  #pragma unroll
+  for (int t = 0; t < 3; t++) {
+    const double lo = (double)cc[t] * sz - slack, hi = (double)(cc[t] + 1u) * sz + slack;
+    const double d = fmax(fmax(lo - rel[t], rel[t] - hi), 0.0);
+    d2 += d * d;
+  }
+  return d2;
+}
+
+// the k-th distance as a pruning bound: a candidate whose FLOAT distance ties or beats it lies at a true distance within a few ulp of it
+__device__ __forceinline__ double prune_bound(unsigned long long kth) {
+  return kth == KEY_INF ? 1e300 : (double)__uint_as_float((unsigned)(kth >> 32)) * (1.0 + 1e-6);
+}
+
+// lane c < 32 may own one covering cell (lo, cnt, cx, cy, cz at shift sh); `top` holds the window's result. Positions inside the window
+// [wlo, wlo + wcnt) are in the list already and are skipped.
+__device__ unsigned long long knn_warp_descent(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes, int k, const Quant& qn,
+                                               const float4 q, int wlo, int wcnt, unsigned long long top, DescItem* stack,
+                                               int lo, int cnt, unsigned cx, unsigned cy, unsigned cz, int sh) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  unsigned ix, iy, iz;
-  quantize(qn, q.x, q.y, q.z, ix, iy, iz);
-  const unsigned long long cq = __ldg(codes + j);
-  int L;
+  const double rel[3] = {(double)q.x - qn.mn[0], (double)q.y - qn.mn[1], (double)q.z - qn.mn[2]};
+  int sp;
   {
-    // the level-cpl(code[j], code[j-4]) cell holds the sorted entries j-4..j (likewise on the right), so the
-    // larger of the two common prefixes is a boundary-robust first guess
-    const unsigned long long xl = cq ^ __ldg(codes + max(j - 4, 0)), xr = cq ^ __ldg(codes + min(j + 4, n - 1));
-    const int bl = (j - 4 >= 0) ? (xl ? (__clzll((long long)xl) - (64 - CODE_BITS)) : CODE_BITS) : 0;
-    const int br = (j + 4 < n) ? (xr ? (__clzll((long long)xr) - (64 - CODE_BITS)) : CODE_BITS) : 0;
-    L = min(max(bl, br) / 3, MORTON_BITS);
+    const double bound0 = prune_bound(__shfl_sync(FULL, top, k - 1));   // every lane takes part in the shuffle
+    const double m2 = cnt > 0 ? cell_min_d2(qn, rel, cx, cy, cz, sh) : 0.0;
+    const bool valid = cnt > 0 && m2 <= bound0;
+    const unsigned vm = __ballot_sync(FULL, valid);
+    int r = 0;                                           // farther valid cells go below this one
+    #pragma unroll 4
+    for (int s2 = 0; s2 < 32; s2++) {
+      const double o = __shfl_sync(FULL, m2, s2);
+      if (((vm >> s2) & 1u) && (o > m2 || (o == m2 && s2 > lane))) r++;
+    }
+    if (valid) { DescItem it; it.lo = lo; it.cnt = cnt; it.cell = (unsigned long long)cx | ((unsigned long long)cy << 13) | ((unsigned long long)cz << 26) | ((unsigned long long)sh << 39); stack[r] = it; }
+    sp = __popc(vm);
+    __syncwarp();
   }
-  unsigned long long top = KEY_INF;                   // this lane's element of the sorted top-32
-  bool no_finer = false;
+  int splits = 0;                                       // bounded: past the budget the remaining cells are scanned as they are
   #pragma unroll 1
-  for (;;) {
-    const int sh = MORTON_BITS - L;
-    const int cx = (int)(ix >> sh), cy = (int)(iy >> sh), cz = (int)(iz >> sh);
-    const int ncell = 1 << L;
-    int lo = 0, cnt = 0;
-    if (lane < 27) {
-      const int oo = (lane == 0) ? 13 : (lane <= 13 ? lane - 1 : lane);   // centre cell first
-      const int nx = cx + oo % 3 - 1, ny = cy + (oo / 3) % 3 - 1, nz = cz + oo / 9 - 1;
-      if (nx >= 0 && ny >= 0 && nz >= 0 && nx < ncell && ny < ncell && nz < ncell) {
-        const unsigned long long pre = morton3((unsigned)nx, (unsigned)ny, (unsigned)nz);
-        lo = lower_bound_bucketed(codes, bucket_start, pre << (3 * sh));
-        const int hi = (L == 0) ? n : lower_bound_bucketed(codes, bucket_start, (pre + 1ull) << (3 * sh));
-        cnt = hi - lo;
+  while (sp > 0) {
+    sp--;
+    const DescItem it = stack[sp];                       // every lane reads the same entry
+    __syncwarp();
+    const unsigned icx = (unsigned)(it.cell & 0x1FFFu), icy = (unsigned)((it.cell >> 13) & 0x1FFFu), icz = (unsigned)((it.cell >> 26) & 0x1FFFu);
+    const int ish = (int)(it.cell >> 39);
+    const double bound = prune_bound(__shfl_sync(FULL, top, k - 1));
+    if (cell_min_d2(qn, rel, icx, icy, icz, ish) > bound) continue;
+    if (it.cnt <= KNN_DESC_LEAF || ish == 0 || sp + 8 > KNN_DESC_STACK || ++splits > KNN_DESC_SPLITS) {
+      #pragma unroll 1
+      for (int base = 0; base < it.cnt; base += 32) {
+        const int pos = it.lo + base + lane;
+        unsigned long long key = KEY_INF;
+        if (base + lane < it.cnt && (unsigned)(pos - wlo) >= (unsigned)wcnt) {
+          const float4 p = __ldg(sorted + pos);
+          const float d = dist2_exact(q, p);
+          if (d == d) key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+        }
+        knn_warp_merge(top, key, k, false);
       }
+      continue;
     }
-    int incl = cnt;
+    // split: the children are consecutive in Morton order, child c (x bit 0, y bit 1, z bit 2) = [b_c, b_(c+1))
+    const unsigned long long P = morton3(icx, icy, icz);
+    int b = lane == 0 ? it.lo : it.lo + it.cnt;
+    if (lane >= 1 && lane <= 7) {
+      const unsigned long long key = ((P << 3) + (unsigned long long)lane) << (3 * (ish - 1));
+      int l2 = it.lo, h2 = it.lo + it.cnt;
+      while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (__ldg(codes + mid) < key) l2 = mid + 1; else h2 = mid; }
+      b = l2;
+    }
+    const int bn = __shfl_down_sync(FULL, b, 1);
+    const int ccnt = lane < 8 ? bn - b : 0;
+    const unsigned ccx = 2u * icx + (lane & 1), ccy = 2u * icy + ((lane >> 1) & 1), ccz = 2u * icz + ((lane >> 2) & 1);
+    const double m2 = ccnt > 0 ? cell_min_d2(qn, rel, ccx, ccy, ccz, ish - 1) : 0.0;
+    const bool valid = ccnt > 0 && m2 <= bound;
+    const unsigned vm = __ballot_sync(FULL, valid);
+    int r = 0;
     #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
-    const int total = __shfl_sync(FULL, incl, 31);
-    if (!no_finer && total > KNN_CAND_CAP && L < MORTON_BITS) { L++; continue; }
-    if (total < k && L > 0) { no_finer = true; L--; continue; }
-    const int excl = incl - cnt;
-
-    top = KEY_INF;
-    #pragma unroll 1
-    for (int base = 0; base < total; base += 32) {
-      const int g = base + lane;
-      const bool valid = g < total;
-      int a = 0, b = 26;                                // owning cell: the first lane whose inclusive count exceeds g
-      #pragma unroll
-      for (int s = 0; s < 5; s++) {
-        const int mid = (a + b) >> 1;
-        const int v = __shfl_sync(FULL, incl, mid);
-        if (v <= g) a = mid + 1; else b = mid;
-      }
-      a = min(a, 26);
-      const int cell_lo = __shfl_sync(FULL, lo, a), cell_ex = __shfl_sync(FULL, excl, a);
-      unsigned long long key = KEY_INF;
-      if (valid) {
-        const float4 p = __ldg(sorted + cell_lo + (g - cell_ex));
-        const float d = dist2_exact(q, p);
-        if (d == d) key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
-      }
-      const unsigned long long kth = __shfl_sync(FULL, top, k - 1);
-      const bool pass = key < kth;
-      unsigned m = __ballot_sync(FULL, pass);
-      if (m == 0) continue;
-      if (__popc(m) > 10) {
-        // bitonic sort of the batch (non-passing lanes carry +inf), then bitonic merge with the top-32
-        if (!pass) key = KEY_INF;
-        #pragma unroll
-        for (int k2 = 2; k2 <= 32; k2 <<= 1) {
-          #pragma unroll
-          for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) bitonic_cmpx(key, j2, ((lane & k2) == 0) == ((lane & j2) == 0));
-        }
-        if (base == 0) {
-          top = key;                                   // the top-32 is still empty: the sorted batch is the new top-32
-        } else {
-          const unsigned long long rev = __shfl_sync(FULL, key, 31 - lane);
-          if (rev < top) top = rev;
-          #pragma unroll
-          for (int j2 = 16; j2 > 0; j2 >>= 1) bitonic_cmpx(top, j2, (lane & j2) == 0);
-        }
-      } else {
-        while (m) {
-          const int srcl = __ffs(m) - 1;
-          m &= m - 1;
-          const unsigned long long ck = __shfl_sync(FULL, key, srcl);
-          const int pos = __popc(__ballot_sync(FULL, top < ck));      // elements that stay in front
-          const unsigned long long up = __shfl_up_sync(FULL, top, 1);
-          if (lane > pos) top = up; else if (lane == pos) top = ck;
-        }
-      }
+    for (int s2 = 0; s2 < 8; s2++) {
+      const double o = __shfl_sync(FULL, m2, s2);
+      if (((vm >> s2) & 1u) && (o > m2 || (o == m2 && s2 > lane))) r++;
     }
-    if (L == 0) break;
-    // exact iff the k-th neighbour lies inside the guaranteed-complete radius of the scanned block
-    const double sL = qn.cell * (double)(1 << sh);
-    const double rel[3] = {(double)q.x - qn.mn[0], (double)q.y - qn.mn[1], (double)q.z - qn.mn[2]};
-    double rs = 1e300;
-    const int cc[3] = {cx, cy, cz};
-    #pragma unroll
-    for (int dd = 0; dd < 3; dd++) {
-      if (cc[dd] - 1 >= 0) rs = fmin(rs, rel[dd] - (double)(cc[dd] - 1) * sL);
-      if (cc[dd] + 1 < ncell) rs = fmin(rs, (double)(cc[dd] + 2) * sL - rel[dd]);
-    }
-    const unsigned long long kth = __shfl_sync(FULL, top, k - 1);
-    if (kth != KEY_INF && (double)__uint_as_float((unsigned)(kth >> 32)) <= rs * rs * (1.0 - 1e-6)) break;
-    no_finer = true;
-    L--;
+    if (valid) { DescItem ch; ch.lo = b; ch.cnt = ccnt; ch.cell = (unsigned long long)ccx | ((unsigned long long)ccy << 13) | ((unsigned long long)ccz << 26) | ((unsigned long long)(ish - 1) << 39); stack[sp + r] = ch; }
+    sp += __popc(vm);
+    __syncwarp();
   }
   return top;
 }
 
-
 __device__ unsigned long long knn_warp_query(const float4* __restrict__ sorted, const unsigned long long* __restrict__ codes,
-                                             const int* __restrict__ bucket_start, int n, int k, const Quant& qn, int j, const float4 q) {
+                                             const int* __restrict__ bucket_start, int n, int k, const Quant& qn, int j, const float4 q,
+                                             DescItem* __restrict__ stack) {
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   unsigned long long top = KEY_INF;                   // this lane's element of the sorted top-32
@@ -808,13 +798,14 @@ __device__ unsigned long long knn_warp_query(const float4* __restrict__ sorted, 
   const float R = __fmul_ru(__fsqrt_ru(tau), 1.000001f);
   const float lox = __fsub_rd(q.x, R), loy = __fsub_rd(q.y, R), loz = __fsub_rd(q.z, R);
   const float hix = __fadd_ru(q.x, R), hiy = __fadd_ru(q.y, R), hiz = __fadd_ru(q.z, R);
-  int lo = 0, cnt = 0;
+  int lo = 0, cnt = 0, sh;
+  unsigned cx = 0, cy = 0, cz = 0;
   {
     unsigned ix0, iy0, iz0, ix1, iy1, iz1;
     quantize(qn, lox, loy, loz, ix0, iy0, iz0);
     quantize(qn, hix, hiy, hiz, ix1, iy1, iz1);
     const unsigned ext = max(max(ix1 - ix0, iy1 - iy0), iz1 - iz0);
-    int sh = max(0, 30 - __clz((int)ext));
+    sh = max(0, 30 - __clz((int)ext));
     int ncx, ncy, ncz;
     #pragma unroll 1
     for (;; sh++) {
@@ -822,7 +813,7 @@ __device__ unsigned long long knn_warp_query(const float4* __restrict__ sorted, 
       if (ncx * ncy * ncz <= 32 || sh >= MORTON_BITS) break;
     }
     if (lane < ncx * ncy * ncz) {
-      const unsigned cx = (ix0 >> sh) + (unsigned)(lane % ncx), cy = (iy0 >> sh) + (unsigned)((lane / ncx) % ncy), cz = (iz0 >> sh) + (unsigned)(lane / (ncx * ncy));
+      cx = (ix0 >> sh) + (unsigned)(lane % ncx); cy = (iy0 >> sh) + (unsigned)((lane / ncx) % ncy); cz = (iz0 >> sh) + (unsigned)(lane / (ncx * ncy));
       const unsigned long long pre = morton3(cx, cy, cz);
       lo = lower_bound_bucketed(codes, bucket_start, pre << (3 * sh));
       const int hi = (sh >= MORTON_BITS) ? n : lower_bound_bucketed(codes, bucket_start, (pre + 1ull) << (3 * sh));
@@ -834,7 +825,7 @@ __device__ unsigned long long knn_warp_query(const float4* __restrict__ sorted, 
   for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, incl, off); if (lane >= off) incl += v; }
   const int total = __shfl_sync(FULL, incl, 31);
   const int excl = incl - cnt;
-  if (total > KNN_BOX_CAP) return knn_warp_query_levels(sorted, codes, bucket_start, n, k, qn, j, q);   // loose bound (a jump of the Morton curve)
+  if (total > KNN_DESC_MIN) return knn_warp_descent(sorted, codes, k, qn, q, wlo, wcnt, top, stack, lo, cnt, cx, cy, cz, sh);
   #pragma unroll 1
   for (int base = 0; base < total; base += 32) {
     const int g = base + lane;
@@ -865,6 +856,7 @@ __device__ unsigned long long knn_warp_query(const float4* __restrict__ sorted, 
 __global__ void __launch_bounds__(256)
 knn_fallback_kernel(const KnnCloud* __restrict__ clouds, const float4* __restrict__ sorted_all, const unsigned long long* __restrict__ codes_all,
                     const int* __restrict__ bucket_all, const int* __restrict__ bbox_all, const int* __restrict__ fail, int k, int method) {
+  __shared__ DescItem desc_stack[8][KNN_DESC_STACK];
   const unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int nfail = fail[0];
@@ -877,7 +869,7 @@ knn_fallback_kernel(const KnnCloud* __restrict__ clouds, const float4* __restric
     const Quant qn = make_quant(bbox_all + cloud * 8);
     const float4 q = __ldg(sorted + j);
     const int self = __float_as_int(q.w);
-    const unsigned long long top = knn_warp_query(sorted, codes_all + C.off, bucket_all + (size_t)cloud * (N_BUCKETS + 1), C.n, k, qn, j, q);
+    const unsigned long long top = knn_warp_query(sorted, codes_all + C.off, bucket_all + (size_t)cloud * (N_BUCKETS + 1), C.n, k, qn, j, q, desc_stack[threadIdx.x >> 5]);
     const bool mine = lane < k;
     const unsigned idx = (unsigned)(top & 0xFFFFFFFFull);
     const bool good = !mine || (top != KEY_INF && idx < (unsigned)C.n);
