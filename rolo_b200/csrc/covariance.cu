@@ -6,22 +6,28 @@
 //   1. per cloud bounding box, 39-bit Morton codes (13 bits/axis), ONE radix sort of (cloud id | code, index) over the
 //      concatenated group [cub::DeviceRadixSort is the only library call: plumbing, not the hot op], Morton-ordered copy of the
 //      points, bucket table over the top code bits.
-//   2. knn_chunk_kernel: one WARP owns 32 Morton-consecutive queries (one per lane) and searches them TOGETHER:
-//        a. each lane bounds its k-th neighbour distance by the k Morton-order neighbours on its left, around it and on its right
-//           (3 windows, the smallest maximum): tau0;
-//        b. the union of the 32 balls (q, sqrt(tau0)) gives one box; the box is covered by <= 32 octree cells of one level,
-//           each cell is one contiguous range of the sorted array (one bucketed binary-search pair per LANE, not per query);
-//        c. the candidates of those ranges are clipped against the box and staged in shared memory once; every lane scans
-//           all of them (broadcast reads), keeping the k smallest DISTANCES in registers as a sorted min/max chain
-//           (2 FMNMX per slot, no index payload, no divergence) and appending the position of every candidate that was at
-//           most the running k-th distance to a per-lane pass list in shared memory;
+//   2. knn_chunk_kernel: one WARP owns 32 Morton-consecutive queries (one per lane) and searches them TOGETHER; persistent warps draw
+//      chunks from a global ticket:
+//        a. the 64 Morton-order neighbours of the chunk are staged once; every lane visits them outwards from its own position. The
+//           k smallest DISTANCES live in registers as an ascending list (no index payload), updated in batches by sort-merge on a
+//           comparator network (sort_networks.cuh); the window's k-th distance tau0 bounds the lane's search radius;
+//        b. consecutive lanes whose balls' boxes are disjoint share no candidate: the chunk is cut into groups there. Per group the
+//           union box is covered by <= 32 octree cells of one level, each one contiguous range of the sorted array (one bucketed
+//           binary-search pair per LANE, not per query); a group whose cells hold more than KNN_RAW_CAP points sheds its widest
+//           lanes to the fallback kernel;
+//        c. the candidates of those ranges are clipped against the box and staged in shared memory; every lane scans all of them
+//           (broadcast reads) against its fixed threshold tau0 and records position + distance of what passes in a per-lane list
+//           in shared memory; the list is merged into the distance list once at the end (a list that runs full is brought up to
+//           date early);
 //        d. tau* = the exact k-th smallest distance. The neighbour SET is {d < tau*} plus the (k - m) smallest original
-//           indices among {d == tau*}, taken from the pass list: the same set the oracle's (distance, index) order selects;
+//           indices among {d == tau*}, taken from the window flags and the pass list: the same set the oracle's (distance, index)
+//           order selects;
 //        e. epilogue in the same kernel: mean / scatter in fp64, cyclic-Jacobi eigen-decomposition, regulariser, tile-planar
 //           fp32 store. The neighbour lists (21 MB per 262144-point cloud) are never written.
-//      Anything unusual (pass-list or tie overflow, non-finite query) puts the query on a fail list;
-//   3. knn_fallback_kernel serves that list with the warp-per-query octree search (sorted top-32 across the lanes) + the same
-//      epilogue. It is the slow exact path, normally empty.
+//      Anything unusual (shed lanes, pass-list or tie overflow, non-finite query) puts the query on a fail list;
+//   3. knn_fallback_kernel serves that list one warp per query (sorted top-32 across the lanes): Morton window, then the covering
+//      cells of the ball's box — scanned directly when small, else refined by an octree descent with distance pruning (per-warp
+//      stack, nearest cell first) — + the same epilogue. 0.3-0.9 % of the queries.
 // Float distances are accumulated x,y,z without FMA contraction so the neighbour sets match the CPU oracle bit for bit.
 
 #include "covariance.cuh"
@@ -248,7 +254,10 @@ constexpr int KNN_STAGE = 128;        // staged candidates per warp (float4), + 
 constexpr int KNN_PL = 28;            // per-lane list of (position, distance): a window phase queues <= 22 distances, the region phase
                                       // records the candidates within the window's k-th distance
 constexpr int KNN_TIE = 16;           // tie entries per lane (aliases the stage buffer: 128 float4 = 16 x 32 ints)
-constexpr int KNN_RAW_CAP = 3072;     // candidates of one group before clipping; above it the widest lanes go to the fallback kernel
+#ifndef ROLO_KNN_RAW_CAP
+#define ROLO_KNN_RAW_CAP 4096
+#endif
+constexpr int KNN_RAW_CAP = ROLO_KNN_RAW_CAP;     // candidates of one group before clipping; above it the widest lanes go to the fallback kernel
 constexpr int KNN_WINDOW = 64;        // Morton-order neighbours scanned first (the chunk itself + 16 before + 16 after)
 constexpr int KNN_FILL = 20;          // window entries visited before the first list update (every lane's nearest Morton neighbours)
 constexpr size_t KNN_STAGE_BYTES = (KNN_STAGE + 4) * sizeof(float4);
@@ -669,9 +678,15 @@ __device__ __forceinline__ void knn_warp_merge(unsigned long long& top, unsigned
 // per lane), which are pushed farthest first. The k-th distance shrinks as the near cells are scanned, so a stray point beside a dense
 // surface touches the few hundred candidates around its neighbours instead of the thousands inside its first box.
 constexpr int KNN_DESC_STACK = 160;   // 32 covering cells + 7 per level of refinement (13 levels)
-constexpr int KNN_DESC_LEAF = 128;    // cells up to this size are scanned, larger ones split
+#ifndef ROLO_KNN_DESC_LEAF
+#define ROLO_KNN_DESC_LEAF 128
+#endif
+#ifndef ROLO_KNN_DESC_MIN
+#define ROLO_KNN_DESC_MIN 512
+#endif
+constexpr int KNN_DESC_LEAF = ROLO_KNN_DESC_LEAF;    // cells up to this size are scanned, larger ones split
 constexpr int KNN_DESC_SPLITS = 4096; // splits per query before the descent stops refining (a guard, never reached on real clouds)
-constexpr int KNN_DESC_MIN = 512;     // covering cells holding at most this many points are scanned directly (no stack)
+constexpr int KNN_DESC_MIN = ROLO_KNN_DESC_MIN;     // covering cells holding at most this many points are scanned directly (no stack)
 
 struct DescItem { int lo, cnt; unsigned long long cell; };   // cell = cx | cy << 13 | cz << 26 | shift << 39
 
