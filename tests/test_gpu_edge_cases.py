@@ -63,6 +63,28 @@ def test_duplicate_points_tie_break():
     assert np.array_equal(o.knn(1, 20), g.knn(capi.TARGET, 20))
 
 
+def test_stray_points_beside_dense_surfaces_take_the_descent_fallback():
+    """The geometry the warp-per-query fallback exists for (covariance.cu, knn_warp_descent): stray points whose Morton neighbours are far
+    away sit beside surfaces sampled at 1 cm, so the ball of the window bound holds thousands of candidates although the answer is twenty.
+    A wall, a dense blob, a pile of 700 exact duplicates (a finest cell holding more points than a leaf: the shift-0 branch) and strays at all
+    distances; neighbour lists must equal the oracle's on EVERY point, for k = 20 and for k = 32 (the top-32 completely in use)."""
+    rng = np.random.default_rng(77)
+    yy, zz = np.meshgrid(np.arange(0.0, 4.0, 0.01), np.arange(0.0, 2.0, 0.01), indexing="ij")
+    wall = np.stack([np.full(yy.size, 5.0), yy.ravel(), zz.ravel()], axis=1) + rng.normal(0, 0.002, (yy.size, 3))
+    blob = rng.uniform(0, 0.2, (50000, 3)) + np.array([2.0, 7.0, 1.0])
+    dup = np.repeat(np.array([[5.003, 1.2345, 0.777]]), 700, axis=0)                     # 700 identical points inside the wall
+    strays = rng.uniform(0, 10, (3000, 3))
+    near = wall[rng.choice(len(wall), 1500, replace=False)] + rng.normal(0, 1.0, (1500, 3)) * np.array([0.6, 0.05, 0.05])   # off the wall by up to ~1 m
+    pts = np.concatenate([wall, blob, dup, strays, near], axis=0).astype(np.float32)
+    pts = pts[rng.permutation(len(pts))]
+    cloud = np.concatenate([pts, np.ones((len(pts), 1), np.float32)], axis=1)
+    o, g = make_both(cloud, cloud[:4096].copy(), shared_covs=False)
+    for k in (20, 32):
+        a = o.knn(1, k); b = g.knn(capi.TARGET, k)
+        bad = np.flatnonzero(np.any(a != b, axis=1))
+        assert bad.size == 0, f"k={k}: {bad.size} of {len(a)} neighbour lists differ, first at {bad[:5]}"
+
+
 def test_empty_and_too_small_inputs(tiny_pair):
     tgt, src, _ = tiny_pair
     r = RotVGICP(); r.setPolarResolution(0.175, 0.175, 2.0)
