@@ -259,7 +259,10 @@ constexpr int KNN_TIE = 16;           // tie entries per lane (aliases the stage
 #endif
 constexpr int KNN_RAW_CAP = ROLO_KNN_RAW_CAP;     // candidates of one group before clipping; above it the widest lanes go to the fallback kernel
 constexpr int KNN_WINDOW = 64;        // Morton-order neighbours scanned first (the chunk itself + 16 before + 16 after)
-constexpr int KNN_FILL = 20;          // window entries visited before the first list update (every lane's nearest Morton neighbours)
+#ifndef ROLO_KNN_FILL
+#define ROLO_KNN_FILL 20
+#endif
+constexpr int KNN_FILL = ROLO_KNN_FILL;          // window entries visited before the first list update (every lane's nearest Morton neighbours)
 constexpr size_t KNN_STAGE_BYTES = (KNN_STAGE + 4) * sizeof(float4);
 constexpr size_t KNN_SMEM_WARP = KNN_STAGE_BYTES + (size_t)KNN_PL * 32 * (sizeof(int) + sizeof(float));
 constexpr size_t KNN_SMEM = KNN_WARPS * KNN_SMEM_WARP;
@@ -678,6 +681,9 @@ __device__ __forceinline__ void knn_warp_merge(unsigned long long& top, unsigned
 // per lane), which are pushed farthest first. The k-th distance shrinks as the near cells are scanned, so a stray point beside a dense
 // surface touches the few hundred candidates around its neighbours instead of the thousands inside its first box.
 constexpr int KNN_DESC_STACK = 160;   // 32 covering cells + 7 per level of refinement (13 levels)
+#ifndef ROLO_KNN_FALLBACK_GRID
+#define ROLO_KNN_FALLBACK_GRID 592     // CTAs of 8 warps (one query per warp at a time): 4 per SM — the descent waits on dependent loads, more warps hide them
+#endif
 #ifndef ROLO_KNN_DESC_LEAF
 #define ROLO_KNN_DESC_LEAF 128
 #endif
@@ -1197,7 +1203,7 @@ cudaError_t launch_covariances_group(const KnnGroup& g, cudaStream_t stream, int
   else if (g.k <= 24) e = launch_chunk<24>(g, total_chunks, stream);
   else e = launch_chunk<32>(g, total_chunks, stream);
   if (e != cudaSuccess) return e;
-  knn_fallback_kernel<<<296, 256, 0, stream>>>(g.s.clouds, g.s.sorted, g.s.codes_a, g.s.bucket_start, g.s.bbox, g.s.fail, g.k, g.method);
+  knn_fallback_kernel<<<ROLO_KNN_FALLBACK_GRID, 256, 0, stream>>>(g.s.clouds, g.s.sorted, g.s.codes_a, g.s.bucket_start, g.s.bbox, g.s.fail, g.k, g.method);
   if (g.ev_knn1) cudaEventRecord(g.ev_knn1, stream);
   if (own_launches) *own_launches = 7;   // bbox_init, bbox, morton, gather, bucket table, chunk kNN + covariance, fallback (+ 1 memset not counted; cub's kernels not counted)
   return cudaGetLastError();
