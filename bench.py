@@ -287,7 +287,21 @@ def emit(line: dict):
 
 
 def run_sharded(args, rank, world, local_rank):
-    """--mode sharded: BASELINE configs[3], ONE large scan-to-submap registration at a time on all N GPUs (strong scaling): a ~131 k-point
+    """--mode sharded: one JSON line for BASELINE configs[3] (see measure_sharded)."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = measure_sharded(args, rank, world, local_rank, args.steps, args.warmup)
+    if rank == 0:
+        emit(line)
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+def measure_sharded(args, rank, world, local_rank, steps, warmup):
+    """BASELINE configs[3], ONE large scan-to-submap registration at a time on all N GPUs (strong scaling): a ~131 k-point
     live scan against a ~10 M-point submap (77 scans merged in the map frame), UNIFORM 1.0 m voxels, DIRECT7, 20 Gauss-Newton iterations.
     A step = the full registration: covariances of both clouds (target: every rank its slice of the Morton order), voxel sums per rank +
     one all-gather of the compact voxel lists, then 20 fused linearize launches over this rank's block of the source with the 32-double
@@ -299,10 +313,7 @@ def run_sharded(args, rank, world, local_rank):
     from rolo_b200.dist import sharded_registration, shard_bounds
     from rolo_b200.registration import RotVGICP
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    dev = torch.device("cuda", local_rank)                        # the caller has set the device and, for world > 1, initialised the process group
     n_scans, sensor, sigma_map = args.submap_scans, "os1-128x1024", 0.004
     scene = synth.make_scene()
     clouds, poses = [], []
@@ -352,13 +363,13 @@ def run_sharded(args, rank, world, local_rank):
             t = torch.tensor([ms], dtype=torch.float64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
         return ms, L.rg_kernel_launch_count() - l0, out
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step(True)
     step(False)
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    ms, launches, out = timed(True, args.steps)
+    ms, launches, out = timed(True, steps)
     clocks = sampler.stop() if sampler else None
-    ms_e2e, _, _ = timed(False, args.steps)
+    ms_e2e, _, _ = timed(False, steps)
     erot, etr = synth.pose_error(out.astype(np.float64), T_live)
     assert erot < 2e-3 and etr < 3e-2, f"registration failed: {erot} rad {etr} m"      # 1 m voxels over a 77-scan map: centimetre-level agreement with the ground truth
     assert r.nrIterations() == GN_ITERS - 1
@@ -379,25 +390,24 @@ def run_sharded(args, rank, world, local_rank):
         kus = kern_us / reps
         line = {
             "metric": "scan-to-submap registrations/sec (full align: target+source covariances, voxel map, 20 GN iters) @131k-pt scan vs 10M-pt submap",
-            "value": args.steps / (ms * 1e-3), "unit": "registrations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "value": steps / (ms * 1e-3), "unit": "registrations/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"configs[3]: one {n_src}-point OS1-128 scan vs a {n_tgt}-point submap ({n_scans} scans merged), UNIFORM 1.0 m / DIRECT7 / PLANE k=20, GaussNewton x{GN_ITERS}; "
                                    f"target slices + source blocks sharded over {world} GPU(s), voxel lists all-gathered once per align, per-evaluation sums reduced inside the fused kernel over NVLink peer memory",
                        "source_points": n_src, "target_points": n_tgt, "gn_iters": GN_ITERS, "l2": f"inputs larger than L2: {n_tgt * 16 // 2**20} MiB target + {n_tgt * 24 // 2**20} MiB covariances per step",
                        "parallelism": f"sharded-sp{world}"},
             "gn_iters_per_s": 1.0 / t_iter, "gn_iter_us_wall": 1e6 * t_iter, "fused_kernel_us": kus,
             "gpu_launches": int(launches),
-            "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": "registrations/s", "h2d_bytes_per_step": n_src * 16, "d2h_bytes_per_step": GN_ITERS * 32 * 8 + 64,
-                    "ms_per_step": ms_e2e / args.steps, "note": "the live scan is copied from pinned host memory every step; the submap is resident (it persists across frames)"},
+            "e2e": {"value": steps / (ms_e2e * 1e-3), "unit": "registrations/s", "h2d_bytes_per_step": n_src * 16, "d2h_bytes_per_step": GN_ITERS * 32 * 8 + 64,
+                    "ms_per_step": ms_e2e / steps, "note": "the live scan is copied from pinned host memory every step; the submap is resident (it persists across frames)"},
             "roofline": {"bound": "hbm", "kernel": "rolo::linearize_kernel<SE3,refresh,DIRECT7> on this rank's source block", "achieved": algo / (kus * 1e-6) / 1e9 if kus > 0 else None,
                          "peak": peak, "unit": "GB/s", "frac": (algo / (kus * 1e-6) / 1e9 / peak) if kus > 0 else None, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo, "launch_us": kus, "note": "a 131 k-point source is launch/latency bound, not bandwidth bound"},
             "cpu_baseline": None, "clocks": clocks,
             "parity": {"rot_rad_vs_gt": erot, "trans_m_vs_gt": etr},
         }
-        emit(line)
-    if world > 1:
-        dist.barrier(); dist.destroy_process_group()
+        return line
+    return None
 
 
 def main():
@@ -411,7 +421,7 @@ def main():
     ap.add_argument("--mode", default="batch", choices=["batch", "sharded"], help="batch: configs[2] (independent pairs per GPU, headline); sharded: configs[3] (one scan-to-submap registration on all GPUs)")
     ap.add_argument("--submap-scans", type=int, default=77, help="--mode sharded: scans merged into the target (77 = ~10 M points)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the single-pair latency, configs[4] front-end stream and scan-to-map numbers (N = 1 only)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra keys: configs[3] sharded registration on the same GPUs (every N), single-pair latency, configs[4] front-end stream and scan-to-map numbers (N = 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -515,83 +525,107 @@ def main():
     iters_ok = all(batch[i].nrIterations() == GN_ITERS - 1 for i in range(P))
     assert iters_ok, "not every pair ran exactly 20 GN iterations"
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+    def build_line():
+        regs_per_s = world * P * args.steps / (ms * 1e-3)
+        regs_per_s_e2e = world * P * args.steps / (ms_e2e * 1e-3)
+        peak, peak_src = load_peaks()
+        algo_bytes = ALGO_BYTES_PER_POINT * N_POINTS * P
+        achieved = algo_bytes / (lin_us * 1e-6) / 1e9 if lin_us > 0 else None
+        traffic = ncu_traffic()
+        roofline = {"bound": "hbm", "kernel": "rolo::linearize_kernel<SE3,refresh,DIRECT1> (fused correspondence+Mahalanobis+Jacobian+reduction)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                    "traffic": (traffic["dram_bytes_per_point"] * N_POINTS * P) if traffic else None,
+                    "traffic_source": traffic["capture"] if traffic else None,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
+                    "launch_us": lin_us, "launches_timed": lin_n, "points_per_launch": N_POINTS * P}
 
-    regs_per_s = world * P * args.steps / (ms * 1e-3)
-    regs_per_s_e2e = world * P * args.steps / (ms_e2e * 1e-3)
-    peak, peak_src = load_peaks()
-    algo_bytes = ALGO_BYTES_PER_POINT * N_POINTS * P
-    achieved = algo_bytes / (lin_us * 1e-6) / 1e9 if lin_us > 0 else None
-    traffic = ncu_traffic()
-    roofline = {"bound": "hbm", "kernel": "rolo::linearize_kernel<SE3,refresh,DIRECT1> (fused correspondence+Mahalanobis+Jacobian+reduction)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                "traffic": (traffic["dram_bytes_per_point"] * N_POINTS * P) if traffic else None,
-                "traffic_source": traffic["capture"] if traffic else None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes,
-                "launch_us": lin_us, "launches_timed": lin_n, "points_per_launch": N_POINTS * P}
+        # the step's dominant kernel is the exact-kNN + covariance search: instruction-issue bound (candidates live in shared memory / L1),
+        # so it gets two views: the HBM one (40 algorithmic bytes per point) and the issue one (warp instructions per
+        # query from the committed ncu capture x queries / time, against 4 schedulers x SMs x the SM clock seen during the run)
+        kp = knn_profile()
+        knn_s = stages.get("knn_kernels_ms", 0.0) * 1e-3
+        queries = stages.get("covariance_points", 0)
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        issue_peak = 148 * 4 * sm_clock * 1e6
+        roofline_knn = None
+        if knn_s > 0 and queries > 0:
+            hbm_ach = 40.0 * queries / knn_s / 1e9
+            roofline_knn = {"kernel": "rolo::knn_chunk_kernel<20> (+ knn_fallback_kernel): exact 20-NN of 32 Morton-consecutive queries per warp + covariance / regulariser epilogue",
+                            "share_of_step": knn_s / (ms * 1e-3 / args.steps),
+                            "us_per_cloud": 1e6 * knn_s / (queries / N_POINTS),
+                            "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": peak, "unit": "GB/s", "frac": hbm_ach / peak, "algorithmic_bytes_per_point": 40,
+                                    "traffic": (kp["dram_bytes_per_query"] * queries) if kp else None},
+                            "issue": ({"bound": "warp-instruction issue", "achieved": kp["warp_inst_per_query"] * queries / knn_s, "peak": issue_peak, "unit": "warp-inst/s",
+                                       "frac": kp["warp_inst_per_query"] * queries / knn_s / issue_peak, "warp_inst_per_query": kp["warp_inst_per_query"],
+                                       "source": kp["capture"]} if kp else None)}
 
-    # the step's dominant kernel is the exact-kNN + covariance search: instruction-issue bound (candidates live in shared memory / L1),
-    # so it gets two views: the HBM one (40 algorithmic bytes per point) and the issue one (warp instructions per
-    # query from the committed ncu capture x queries / time, against 4 schedulers x SMs x the SM clock seen during the run)
-    kp = knn_profile()
-    knn_s = stages.get("knn_kernels_ms", 0.0) * 1e-3
-    queries = stages.get("covariance_points", 0)
-    sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
-    issue_peak = 148 * 4 * sm_clock * 1e6
-    roofline_knn = None
-    if knn_s > 0 and queries > 0:
-        hbm_ach = 40.0 * queries / knn_s / 1e9
-        roofline_knn = {"kernel": "rolo::knn_chunk_kernel<20> (+ knn_fallback_kernel): exact 20-NN of 32 Morton-consecutive queries per warp + covariance / regulariser epilogue",
-                        "share_of_step": knn_s / (ms * 1e-3 / args.steps),
-                        "us_per_cloud": 1e6 * knn_s / (queries / N_POINTS),
-                        "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": peak, "unit": "GB/s", "frac": hbm_ach / peak, "algorithmic_bytes_per_point": 40,
-                                "traffic": (kp["dram_bytes_per_query"] * queries) if kp else None},
-                        "issue": ({"bound": "warp-instruction issue", "achieved": kp["warp_inst_per_query"] * queries / knn_s, "peak": issue_peak, "unit": "warp-inst/s",
-                                   "frac": kp["warp_inst_per_query"] * queries / knn_s / issue_peak, "warp_inst_per_query": kp["warp_inst_per_query"],
-                                   "source": kp["capture"]} if kp else None)}
+        cpu = None
+        cpu_parity = None
+        if not args.no_cpu_baseline:
+            hosts = [(tgt_host[i].numpy(), src_host[i].numpy()) for i in range(min(P, 2))]
+            cpu, poses = cpu_baseline_sample(hosts)
+            d = [synth.pose_error(poses[i], out[i].astype(np.float64)) for i in range(min(len(poses), len(hosts)))]
+            cpu_parity = {"max_rot_rad_vs_oracle": max(x[0] for x in d), "max_trans_m_vs_oracle": max(x[1] for x in d)}
 
-    cpu = None
-    cpu_parity = None
-    if not args.no_cpu_baseline:
-        hosts = [(tgt_host[i].numpy(), src_host[i].numpy()) for i in range(min(P, 2))]
-        cpu, poses = cpu_baseline_sample(hosts)
-        d = [synth.pose_error(poses[i], out[i].astype(np.float64)) for i in range(min(len(poses), len(hosts)))]
-        cpu_parity = {"max_rot_rad_vs_oracle": max(x[0] for x in d), "max_trans_m_vs_oracle": max(x[1] for x in d)}
+        line = {
+            "metric": "scan registrations/sec @128x2048 pts (full align: kNN covariances + voxel map + 20 GN iters)",
+            "value": regs_per_s, "unit": "registrations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[1] scan pair (two 128x2048 OS1-128 clouds, GaussNewton x{GN_ITERS}) x {P} pairs per GPU per step, sharded per GPU without collectives (configs[2])",
+                       "pairs_per_gpu": P, "points_per_cloud": N_POINTS, "gn_iters": GN_ITERS, "voxel": "POLAR(0.175,0.175,2.0) DIRECT1 PLANE k=20",
+                       "l2": f"inputs larger than L2: {P} pairs x ~25 MB streamed per GN iteration, ~{P * 85} MB working set per step",
+                       "parallelism": f"batch-dp{world}"},
+            "gn_iters_per_s": regs_per_s * GN_ITERS,
+            "gpu_launches": int(launches),
+            "e2e": {"value": regs_per_s_e2e, "unit": "registrations/s",
+                    "h2d_bytes_per_step": int(P * 2 * N_POINTS * 16), "d2h_bytes_per_step": int(P * (GN_ITERS * 32 * 8 + 64)),
+                    "ms_per_step": ms_e2e / args.steps},
+            "e2e_pageable": {"value": world * P * args.steps / (ms_page * 1e-3), "unit": "registrations/s", "ms_per_step": ms_page / args.steps,
+                             "note": "same as e2e but from ordinary pageable host memory (what a pcl::PointCloud holds): the runtime stages every copy"},
+            "stages_ms_per_step": {**{k: v for k, v in stages.items() if k.endswith("_ms")},
+                                   "other_ms": ms / args.steps - stages.get("covariances_ms", 0) - stages.get("voxel_maps_ms", 0) - stages.get("iterations_ms", 0),
+                                   "note": "CUDA events on the batch stream; covariances = index build (bbox, Morton codes, radix sort, gather, bucket table) + search kernels + epilogue; "
+                                           "iterations = 20 fused launches + the host's 6x6 solves for every pair; other = installing the inputs"},
+            "roofline": roofline,
+            "roofline_knn": roofline_knn,
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "parity": {"max_rot_rad_vs_gt": max_rot, "max_trans_m_vs_gt": max_tr, **(cpu_parity or {})},
+        }
+        if not args.no_extras and world == 1:
+            line["single_pair"] = single_pair_latency(tgt_dev[0], src_dev[0], capi)
+            line["configs5_frontend_stream"] = run_tool("bench_frontend_stream.py", ["os1-128", "20", "--no-cpu"])
+            line["f3_scan2map"] = run_tool("bench_scan2map.py", ["12", "20", "--no-cpu"])
+        return line
 
-    line = {
-        "metric": "scan registrations/sec @128x2048 pts (full align: kNN covariances + voxel map + 20 GN iters)",
-        "value": regs_per_s, "unit": "registrations/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"configs[1] scan pair (two 128x2048 OS1-128 clouds, GaussNewton x{GN_ITERS}) x {P} pairs per GPU per step, sharded per GPU without collectives (configs[2])",
-                   "pairs_per_gpu": P, "points_per_cloud": N_POINTS, "gn_iters": GN_ITERS, "voxel": "POLAR(0.175,0.175,2.0) DIRECT1 PLANE k=20",
-                   "l2": f"inputs larger than L2: {P} pairs x ~25 MB streamed per GN iteration, ~{P * 85} MB working set per step",
-                   "parallelism": f"batch-dp{world}"},
-        "gn_iters_per_s": regs_per_s * GN_ITERS,
-        "gpu_launches": int(launches),
-        "e2e": {"value": regs_per_s_e2e, "unit": "registrations/s",
-                "h2d_bytes_per_step": int(P * 2 * N_POINTS * 16), "d2h_bytes_per_step": int(P * (GN_ITERS * 32 * 8 + 64)),
-                "ms_per_step": ms_e2e / args.steps},
-        "e2e_pageable": {"value": world * P * args.steps / (ms_page * 1e-3), "unit": "registrations/s", "ms_per_step": ms_page / args.steps,
-                         "note": "same as e2e but from ordinary pageable host memory (what a pcl::PointCloud holds): the runtime stages every copy"},
-        "stages_ms_per_step": {**{k: v for k, v in stages.items() if k.endswith("_ms")},
-                               "other_ms": ms / args.steps - stages.get("covariances_ms", 0) - stages.get("voxel_maps_ms", 0) - stages.get("iterations_ms", 0),
-                               "note": "CUDA events on the batch stream; covariances = index build (bbox, Morton codes, radix sort, gather, bucket table) + search kernels + epilogue; "
-                                       "iterations = 20 fused launches + the host's 6x6 solves for every pair; other = installing the inputs"},
-        "roofline": roofline,
-        "roofline_knn": roofline_knn,
-        "cpu_baseline": cpu,
-        "clocks": clocks,
-        "parity": {"max_rot_rad_vs_gt": max_rot, "max_trans_m_vs_gt": max_tr, **(cpu_parity or {})},
-    }
-    if not args.no_extras and world == 1:
-        line["single_pair"] = single_pair_latency(tgt_dev[0], src_dev[0], capi)
-        line["configs5_frontend_stream"] = run_tool("bench_frontend_stream.py", ["os1-128", "20", "--no-cpu"])
-        line["f3_scan2map"] = run_tool("bench_scan2map.py", ["12", "20", "--no-cpu"])
-    emit(line)
+    line = build_line() if rank == 0 else None
+    if not args.no_extras:
+        # configs[3] on the same N GPUs (one scan-to-submap registration sharded over all ranks; `--mode sharded` is the full report): every
+        # rank takes part. A watchdog keeps the headline line safe: if the extra does not come back, rank 0 prints the line without it.
+        import threading
+
+        def bail():
+            if rank == 0:
+                line["configs3_sharded"] = {"error": "no result within 300 s"}
+                emit(line)
+            os._exit(0)
+        wd = threading.Timer(300.0, bail); wd.daemon = True; wd.start()
+        failed = False
+        try:
+            full = measure_sharded(args, rank, world, local_rank, 5, 3)
+            extra = None if full is None else {k: full[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "gn_iters_per_s", "gn_iter_us_wall",
+                                                                    "fused_kernel_us", "gpu_launches", "e2e", "parity")} | {"workload": full["config"]["workload"]}
+        except Exception as e:                                     # the headline number must not depend on the extra
+            extra = {"error": repr(e)}; failed = True
+        wd.cancel()
+        if rank == 0:
+            line["configs3_sharded"] = extra
+            emit(line)
+        if failed:
+            os._exit(0)                                            # peers may be inside a collective this rank will never enter: leave without a tear-down
+    elif rank == 0:
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
