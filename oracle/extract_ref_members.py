@@ -4,10 +4,11 @@
 src/backMapping.cpp needs roscpp, tf, GTSAM, small_gicp and PCL's I/O to compile as a file; the scan-to-map member functions this
 repository restates (SURVEY.md §8 f3) need only PCL points, a kd-tree, cv::Mat and Eigen. This script finds each named member function
 in the reference file where it lies (by its signature, then by matching braces — no line numbers), and writes their text, unmodified and
-in file order, to an include file under oracle/_ref/ (git-ignored build output). oracle/ref_bm_driver.cpp includes that file inside a
-class that declares the members the functions use. Nothing from the reference is stored in the repository.
+in file order, spliced into the driver source in place of its marker line, to STDOUT — the Makefile pipes that straight into the compiler
+(`g++ -x c++ -`), so the reference text exists only in the pipe: nothing from the reference is stored in the repository or left on disk.
+oracle/ref_bm_driver.cpp is the driver: a class that declares the members the functions use, with the marker where they go.
 
-    extract_ref_members.py <reference .cpp> <output .inc> <signature> [<signature> ...]
+    extract_ref_members.py <reference .cpp> <driver .cpp> <marker text> <signature> [<signature> ...]   > translation unit
 """
 import re
 import sys
@@ -38,15 +39,26 @@ def find_function(lines, signature):
 
 
 def main():
-    src, out, sigs = sys.argv[1], sys.argv[2], sys.argv[3:]
+    src, driver, marker, sigs = sys.argv[1], sys.argv[2], sys.argv[3], sys.argv[4:]
     lines = open(src, encoding="utf-8", errors="replace").read().split("\n")
     spans = sorted(find_function(lines, s) + (s,) for s in sigs)
-    with open(out, "w", encoding="utf-8") as f:
-        f.write(f"// GENERATED at build time from {src} — do not commit. Member functions, verbatim, in file order.\n")
-        for a, b, s in spans:
-            f.write(f"// ---- {s}: lines {a + 1}-{b + 1}\n#line {a + 1} \"{src}\"\n")
-            f.write("\n".join(lines[a:b + 1]) + "\n")
-    print(f"extract_ref_members: {len(spans)} functions -> {out}")
+    body = []
+    for a, b, s in spans:
+        body.append(f"// ---- {s}: lines {a + 1}-{b + 1}\n#line {a + 1} \"{src}\"")
+        body.append("\n".join(lines[a:b + 1]))
+    out = []
+    hits = 0
+    for n, l in enumerate(open(driver, encoding="utf-8").read().split("\n")):
+        if marker in l and not l.lstrip().startswith("//"):
+            hits += 1
+            out.extend(body)
+            out.append(f"#line {n + 2} \"{driver}\"")
+        else:
+            out.append(l)
+    if hits != 1:
+        raise SystemExit(f"extract_ref_members: marker `{marker}` must occur exactly once in {driver} (found {hits})")
+    sys.stdout.write(f"#line 1 \"{driver}\"\n" + "\n".join(out))
+    print(f"extract_ref_members: {len(spans)} functions spliced into {driver}", file=sys.stderr)
 
 
 if __name__ == "__main__":

@@ -3,8 +3,8 @@
 //   combineOptimizationCoeffs, LMOptimization
 // for pinning oracle/scan2map_oracle.cpp. backMapping.cpp cannot be compiled as a file here (roscpp, tf, GTSAM, small_gicp, PCL I/O),
 // so oracle/extract_ref_members.py takes the text of exactly those member functions from the reference file where it lies, at build time,
-// into oracle/_ref/backmapping_members.inc (git-ignored build output), and this file includes it inside a class that declares the members
-// they use — with the reference's own include/rolo/utility.h in front (`using namespace std`, PointType, the overload sets the float /
+// and splices it into this file at the marker below on its way into the compiler (a pipe: the reference text is never written to disk),
+// inside a class that declares the members they use — with the reference's own include/rolo/utility.h in front (`using namespace std`, PointType, the overload sets the float /
 // double promotions depend on). The functions run unmodified. Stand-ins: oracle/ref_shim_bm (kd-tree, cv:: operations, Eigen QR over
 // oracle/s2m_numerics.hpp), oracle/ref_shim_ros (ROS, PCL containers, cv::Mat), oracle/ref_shim (Eigen). Test infrastructure; built only
 // where the reference checkout exists (`make -C oracle ref`), output in oracle/_ref/.
@@ -56,7 +56,7 @@ class ScanToMapMembers {
   bool lm_converged = false;
   void transformUpdate() {}     // IMU roll / pitch fusion and the z clamp (backMapping.cpp:1060-1068): outside the path under test
 
-#include "_ref/backmapping_members.inc"
+ROLO_REFERENCE_MEMBER_FUNCTIONS_GO_HERE   // replaced by extract_ref_members.py in the pipe to the compiler
 };
 #undef Matrix
 

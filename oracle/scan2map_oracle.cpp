@@ -12,7 +12,7 @@
  *
  * PINNING: PINNED to the reference's own code. backMapping.cpp cannot be compiled as a file here (roscpp, tf, GTSAM, small_gicp, PCL I/O
  * are absent), but the member functions above can: oracle/extract_ref_members.py takes their text from the reference file where it lies
- * at build time, oracle/ref_bm_driver.cpp compiles them unmodified (with the reference's include/rolo/utility.h in front) into
+ * at build time and splices it into oracle/ref_bm_driver.cpp in the pipe to the compiler (unmodified, with the reference's include/rolo/utility.h in front):
  * oracle/_ref/librolo_ref_bm.so, and tests/test_scan2map_vs_ref_cpu.py requires this restatement to be BIT-EQUAL to them: selection
  * flags and coefficients per point, every Gauss-Newton pass, the degeneracy projection, the convergence test, the whole
  * scan2MapOptimization trajectory. Both sides share the restated third-party numerics (oracle/s2m_numerics.hpp) and the exact kd-tree;
