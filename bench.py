@@ -561,7 +561,7 @@ def main():
 
         cpu = None
         cpu_parity = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:                   # the CPU arm is timed on rank 0 at N = 1 only (the contract); under torchrun the other ranks would be spinning beside it
             hosts = [(tgt_host[i].numpy(), src_host[i].numpy()) for i in range(min(P, 2))]
             cpu, poses = cpu_baseline_sample(hosts)
             d = [synth.pose_error(poses[i], out[i].astype(np.float64)) for i in range(min(len(poses), len(hosts)))]
